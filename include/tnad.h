@@ -1,0 +1,145 @@
+/*
+ * tnad.h -- C ABI of libtnad_b200.so: the B200 (sm_100a) implementation of the
+ * TRG / CTMRG / iPEPS-energy hot path of under-Peter/TensorNetworkAD.jl.
+ *
+ * The reference is pure Julia and has no FFI boundary of its own; every entry
+ * point below replaces the *body* of one reference function (cited as
+ * file:line into the reference tree) so that the Julia signatures stay as they
+ * are and call in here through `ccall` (see INTEGRATION.md for the stubs).
+ *
+ * Conventions
+ *   - All arrays are caller-owned, column-major (Julia / Fortran order) `double`.
+ *     By default they are HOST pointers: the library copies in and out.  With
+ *     tnad_set_pointer_mode(ctx, TNAD_POINTER_DEVICE) array arguments are device
+ *     pointers on the context's device (scalars and int outputs stay on the host).
+ *   - Every function returns an int status (TNAD_OK == 0).  A human-readable
+ *     message for the last failure is available from tnad_last_error().  No C++
+ *     exception crosses this boundary.
+ *   - One tnad_ctx == one device + one stream + its workspace.  Calls on one
+ *     context are serialised by the caller; different contexts are independent.
+ *     Results are valid on return (synchronous semantics).
+ *   - Tapes are opaque, created by a forward call, consumed by any number of
+ *     backward calls, released with tnad_tape_free.
+ *   - There is no CPU fallback: without a usable sm_100 device tnad_create fails.
+ */
+#ifndef TNAD_H
+#define TNAD_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TNAD_API __attribute__((visibility("default")))
+#else
+#define TNAD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tnad_ctx tnad_ctx;
+typedef struct tnad_tape tnad_tape;
+
+enum {
+  TNAD_OK = 0,
+  TNAD_ERR_ARG = 1,        /* bad argument / dimension mismatch (DimensionMismatch in Julia) */
+  TNAD_ERR_CUDA = 2,       /* CUDA runtime error */
+  TNAD_ERR_NOMEM = 3,      /* device out of memory */
+  TNAD_ERR_NOCONV = 4,     /* Jacobi SVD did not converge */
+  TNAD_ERR_NCCL = 5,
+  TNAD_ERR_INTERNAL = 6
+};
+
+enum { TNAD_POINTER_HOST = 0, TNAD_POINTER_DEVICE = 1 };
+enum { TNAD_ENV_RAW = 0, TNAD_ENV_GIVEN = 1 };
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+TNAD_API int tnad_version(void);
+TNAD_API int tnad_create(int device, tnad_ctx** out);
+TNAD_API int tnad_destroy(tnad_ctx* ctx);
+TNAD_API const char* tnad_last_error(tnad_ctx* ctx);       /* ctx may be NULL: message of a failed tnad_create */
+TNAD_API int tnad_set_pointer_mode(tnad_ctx* ctx, int mode);
+TNAD_API int tnad_synchronize(tnad_ctx* ctx);
+/* counters: kernels launched by this library on ctx since creation / last reset */
+TNAD_API int64_t tnad_launch_count(tnad_ctx* ctx);
+TNAD_API int tnad_reset_launch_count(tnad_ctx* ctx);
+/* device memory helpers for callers that keep inputs resident in HBM (bench `value`) */
+TNAD_API int tnad_dev_alloc(tnad_ctx* ctx, int64_t ndoubles, double** dptr);
+TNAD_API int tnad_dev_free(tnad_ctx* ctx, double* dptr);
+TNAD_API int tnad_dev_upload(tnad_ctx* ctx, double* dptr, const double* host, int64_t ndoubles);
+TNAD_API int tnad_dev_download(tnad_ctx* ctx, double* host, const double* dptr, int64_t ndoubles);
+
+/* ---- L1 building blocks (step-level entry points used by the parity tests) --------------- */
+
+/* OMEinsum pairwise `ein"spec"(A, B)` (every contraction call site of trg.jl:25, ctmrg.jl:130-140,
+ * variationalipeps.jl:52-54 is run as a chain of these).  spec like "iba,ad->ibd"; every label
+ * is one ASCII letter.  C = alpha * contraction + beta * C.  dims are the Julia sizes. */
+TNAD_API int tnad_contract(tnad_ctx* ctx, const char* spec,
+                  const double* A, const int64_t* dimsA, int rankA,
+                  const double* B, const int64_t* dimsB, int rankB,
+                  double alpha, double beta, double* C);
+/* Host-only: the GEMM plan the library would run for `spec` (no GPU needed).  Fills
+ * plan[0..63] (layout documented in csrc/contract.cu) so tests can check the stride algebra. */
+TNAD_API int tnad_contract_plan(const char* spec, const int64_t* dimsA, int rankA,
+                       const int64_t* dimsB, int rankB, int64_t* plan);
+
+/* LinearAlgebra.svd(A) as used at trg.jl:36 and ctmrg.jl:136: thin SVD, A (m x n) = U diag(S) V^T,
+ * k = min(m,n), U m x k, S k (descending), V n x k.  One-sided block Jacobi on the device. */
+TNAD_API int tnad_svd(tnad_ctx* ctx, const double* A, int m, int n, double* U, double* S, double* V,
+             int* sweeps_out /* may be NULL */);
+
+/* trg_svd(t, dmax, tol)  (trg.jl:33-44).  t is (d1,d2,d3,d4); u gets (d1,d2,k), v gets (k,d3,d4);
+ * the buffers must hold dmax columns/rows; *k_out = kept rank. */
+TNAD_API int tnad_trg_svd(tnad_ctx* ctx, const double* t, int d1, int d2, int d3, int d4, int dmax, double tol,
+                 double* u, double* v, int* k_out);
+
+/* svd_back(U,S,V,dU,dS,dV; eta)  (trg.jl:72-105), real case.  U m x k, S k, V n x k; any of the
+ * cotangents may be NULL (`nothing`); dA is m x n. */
+TNAD_API int tnad_svd_back(tnad_ctx* ctx, int m, int n, int k, const double* U, const double* S, const double* V,
+                  const double* dU, const double* dS, const double* dV, double eta, double* dA);
+
+/* ---- TRG (trg.jl:13-30 and its Zygote pullback) ------------------------------------------ */
+/* a is (d0,d1,d2,d3) with d0==d2, d1==d3 (the reference passes 2x2x2x2). tape may be NULL. */
+TNAD_API int tnad_trg_forward(tnad_ctx* ctx, const double* a, int d0, int d1, int chi, int niter, double tol,
+                     double* lnZ, tnad_tape** tape);
+/* da (same shape as a) = dlnZ * d lnZ / d a */
+TNAD_API int tnad_trg_backward(tnad_ctx* ctx, tnad_tape* tape, double dlnZ, double* da);
+TNAD_API int tnad_tape_free(tnad_tape* tape);
+
+/* ---- CTMRG (ctmrg.jl:66-153, fixedpoint.jl:11-41) ---------------------------------------- */
+/* _initializect_square(bulk, Val(:raw), chi)  (ctmrg.jl:74-86) */
+TNAD_API int tnad_ctmrg_init_raw(tnad_ctx* ctx, const double* bulk, int D, int chi, double* corner, double* edge);
+/* one ctmrgstep (ctmrg.jl:126-153): bulk D^4, corner chi^2, edge chi*D*chi; vals has chi*D entries */
+TNAD_API int tnad_ctmrgstep(tnad_ctx* ctx, const double* bulk, int D, int chi,
+                   const double* corner_in, const double* edge_in,
+                   double* corner_out, double* edge_out, double* vals);
+/* ctmrg(rt; tol, maxit) with the reference stop rule (counter from -1). corner/edge are in/out.
+ * steps_done, vals (chi*D) and tape may be NULL. */
+TNAD_API int tnad_ctmrg(tnad_ctx* ctx, const double* bulk, int D, int chi, double* corner, double* edge,
+               double tol, int maxit, int* steps_done, double* vals, tnad_tape** tape);
+/* Unrolled reverse sweep through every executed step.  dcorner/dedge: cotangents of the returned
+ * environment.  dbulk (D^4) is required; dcorner0/dedge0 (cotangents of the initial environment)
+ * may be NULL (the reference marks the initialisation @nograd, autodiff.jl:5). */
+TNAD_API int tnad_ctmrg_backward(tnad_ctx* ctx, tnad_tape* tape, const double* dcorner, const double* dedge,
+                        double* dbulk, double* dcorner0, double* dedge0);
+
+/* ---- iPEPS energy (variationalipeps.jl:28-56, ipeps.jl:32-39) ----------------------------- */
+/* expectationvalue(h, ap, rt): h (s,s,s,s), ap (D,D,D,D,s,s) */
+TNAD_API int tnad_expectationvalue(tnad_ctx* ctx, const double* h, const double* ap, int D, int s,
+                          const double* corner, const double* edge, int chi, double* e);
+/* energy(h, ipeps; chi, tol, maxit) and, when gradA != NULL, its gradient w.r.t. ipeps.bulk
+ * exactly as Zygote + src/autodiff.jl compute it.  A is (d,d,d,d,s). steps_done may be NULL. */
+TNAD_API int tnad_energy(tnad_ctx* ctx, const double* h, const double* A, int d, int s, int chi,
+                double tol, int maxit, double* e, double* gradA, int* steps_done);
+/* magnetisation read-out (exampletensors.jl:63-68): |<env,m>/<env,a>| */
+TNAD_API int tnad_magnetisation_readout(tnad_ctx* ctx, const double* a, const double* m, int D,
+                               const double* corner, const double* edge, int chi, double* mag);
+
+/* ---- timing breakdown of the last energy / ctmrg / trg call (milliseconds, CUDA events) ---- */
+/* keys: 0 total, 1 svd, 2 contractions (forward), 3 backward total, 4 svd_back. */
+TNAD_API int tnad_last_timing(tnad_ctx* ctx, double* ms /* [8] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNAD_H */

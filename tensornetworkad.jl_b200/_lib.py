@@ -1,0 +1,354 @@
+"""ctypes binding of libtnad_b200.so -- the same C ABI a Julia `ccall` shim binds.
+
+Fortran-ordered float64 NumPy arrays stand in for Julia arrays.  There is no fallback:
+if the shared library is missing it is built with nvcc; if no sm_100 device is present
+`Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libtnad_b200.so")
+
+ERRORS = {1: "bad argument", 2: "CUDA error", 3: "out of device memory", 4: "SVD did not converge",
+          5: "NCCL error", 6: "internal error"}
+
+c_double_p = C.POINTER(C.c_double)
+c_int64_p = C.POINTER(C.c_int64)
+c_int_p = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); must list every symbol declared in include/tnad.h
+SIGNATURES = {
+    "tnad_version": (C.c_int, []),
+    "tnad_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "tnad_destroy": (C.c_int, [C.c_void_p]),
+    "tnad_last_error": (C.c_char_p, [C.c_void_p]),
+    "tnad_set_pointer_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "tnad_synchronize": (C.c_int, [C.c_void_p]),
+    "tnad_launch_count": (C.c_int64, [C.c_void_p]),
+    "tnad_reset_launch_count": (C.c_int, [C.c_void_p]),
+    "tnad_dev_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "tnad_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tnad_dev_upload": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int64]),
+    "tnad_dev_download": (C.c_int, [C.c_void_p, c_double_p, C.c_void_p, C.c_int64]),
+    "tnad_contract": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, c_int64_p, C.c_int, C.c_void_p, c_int64_p,
+                                C.c_int, C.c_double, C.c_double, C.c_void_p]),
+    "tnad_contract_plan": (C.c_int, [C.c_char_p, c_int64_p, C.c_int, c_int64_p, C.c_int, c_int64_p]),
+    "tnad_svd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
+    "tnad_trg_svd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                               C.c_void_p, C.c_void_p, c_int_p]),
+    "tnad_svd_back": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "tnad_trg_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                   c_double_p, C.POINTER(C.c_void_p)]),
+    "tnad_trg_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "tnad_tape_free": (C.c_int, [C.c_void_p]),
+    "tnad_ctmrg_init_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tnad_ctmrgstep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, c_double_p]),
+    "tnad_ctmrg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                             c_int_p, c_double_p, C.POINTER(C.c_void_p)]),
+    "tnad_ctmrg_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "tnad_expectationvalue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_int, c_double_p]),
+    "tnad_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                              c_double_p, C.c_void_p, c_int_p]),
+    "tnad_magnetisation_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int, c_double_p]),
+    "tnad_last_timing": (C.c_int, [C.c_void_p, c_double_p]),
+}
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen libtnad_b200.so (building it in-tree with nvcc when absent) and declare all prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        if not build_if_missing:
+            raise OSError(f"{_LIBPATH} is missing; run `python __graft_entry__.py build`")
+        from .build import build_library
+        build_library()
+    lib = C.CDLL(_LIBPATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class TnadError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tnad error {code} ({ERRORS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class DimensionMismatch(ValueError):
+    """Mirror of Julia's DimensionMismatch (ipeps.jl:19-20)."""
+
+
+def farray(x, shape=None):
+    """float64, Fortran-ordered (Julia memory layout) copy/view of x."""
+    a = np.asarray(x, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise DimensionMismatch(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return np.asfortranarray(a)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device + one stream + workspace (tnad_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.tnad_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self.lib.tnad_last_error(None)
+            raise TnadError(rc, msg.decode() if msg else "")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tnad_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.tnad_last_error(self.h)
+            msg = msg.decode() if msg else ""
+            if rc == 1 and ("size of tensor" in msg or "must be" in msg or "mismatch" in msg):
+                raise DimensionMismatch(msg)
+            raise TnadError(rc, msg)
+
+    # ---- misc -----------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.tnad_launch_count(self.h))
+
+    def reset_launch_count(self):
+        self.lib.tnad_reset_launch_count(self.h)
+
+    def last_timing(self):
+        ms = (C.c_double * 8)()
+        self.lib.tnad_last_timing(self.h, ms)
+        return dict(total=ms[0], svd=ms[1], contractions=ms[2], backward=ms[3], svd_back=ms[4])
+
+    def set_pointer_mode(self, mode: int):
+        self.check(self.lib.tnad_set_pointer_mode(self.h, int(mode)))
+
+    def dev_alloc(self, n: int) -> int:
+        p = C.c_void_p()
+        self.check(self.lib.tnad_dev_alloc(self.h, int(n), C.byref(p)))
+        return p.value
+
+    def dev_free(self, p: int):
+        self.check(self.lib.tnad_dev_free(self.h, C.c_void_p(p)))
+
+    def dev_upload(self, p: int, a: np.ndarray):
+        a = farray(a)
+        self.check(self.lib.tnad_dev_upload(self.h, C.c_void_p(p), a.ctypes.data_as(c_double_p), a.size))
+
+    def dev_download(self, p: int, shape) -> np.ndarray:
+        out = np.empty(shape, dtype=np.float64, order="F")
+        self.check(self.lib.tnad_dev_download(self.h, out.ctypes.data_as(c_double_p), C.c_void_p(p), out.size))
+        return out
+
+    # ---- building blocks --------------------------------------------------------------------------
+    def contract(self, spec: str, A, B, alpha=1.0, beta=0.0, Cin=None):
+        A, B = farray(A), farray(B)
+        lhs, out = spec.replace(" ", "").split("->")
+        la, lb = lhs.split(",")
+        ext = {}
+        for l, n in zip(la, A.shape):
+            ext[l] = n
+        for l, n in zip(lb, B.shape):
+            ext[l] = n
+        cshape = tuple(ext[l] for l in out)
+        Cout = farray(Cin, cshape).copy(order="F") if Cin is not None else np.zeros(cshape, order="F")
+        da = (C.c_int64 * A.ndim)(*A.shape)
+        db = (C.c_int64 * B.ndim)(*B.shape)
+        self.check(self.lib.tnad_contract(self.h, spec.encode(), _p(A), da, A.ndim, _p(B), db, B.ndim,
+                                          float(alpha), float(beta), _p(Cout)))
+        return Cout
+
+    def svd(self, A):
+        A = farray(A)
+        m, n = A.shape
+        k = min(m, n)
+        U = np.empty((m, k), order="F"); S = np.empty(k); V = np.empty((n, k), order="F")
+        sw = C.c_int(0)
+        self.check(self.lib.tnad_svd(self.h, _p(A), m, n, _p(U), _p(S), _p(V), C.byref(sw)))
+        self.last_sweeps = sw.value
+        return U, S, V
+
+    def trg_svd(self, t, dmax, tol):
+        t = farray(t)
+        d1, d2, d3, d4 = t.shape
+        kmax = min(dmax, d1 * d2, d3 * d4)
+        u = np.zeros((d1, d2, kmax), order="F"); v = np.zeros((kmax * d3 * d4,), order="F")
+        k = C.c_int(0)
+        self.check(self.lib.tnad_trg_svd(self.h, _p(t), d1, d2, d3, d4, int(dmax), float(tol), _p(u), _p(v),
+                                         C.byref(k)))
+        k = k.value
+        return (np.asfortranarray(u[:, :, :k]),
+                np.reshape(v[: k * d3 * d4], (k, d3, d4), order="F"))
+
+    def svd_back(self, U, S, V, dU=None, dS=None, dV=None, eta=1e-40):
+        U, S, V = farray(U), farray(S), farray(V)
+        m, k = U.shape
+        n = V.shape[0]
+        dU = None if dU is None else farray(dU, (m, k))
+        dS = None if dS is None else farray(dS, (k,))
+        dV = None if dV is None else farray(dV, (n, k))
+        if dU is None and dS is None and dV is None:
+            return None                                     # trg.jl:73
+        dA = np.empty((m, n), order="F")
+        self.check(self.lib.tnad_svd_back(self.h, m, n, k, _p(U), _p(S), _p(V), _p(dU), _p(dS), _p(dV),
+                                          float(eta), _p(dA)))
+        return dA
+
+    # ---- TRG ----------------------------------------------------------------------------------------
+    def trg_forward(self, a, chi, niter, tol=1e-16, want_tape=False):
+        a = farray(a)
+        if a.ndim != 4 or a.shape[0] != a.shape[2] or a.shape[1] != a.shape[3]:
+            raise DimensionMismatch(f"trg needs a (d0,d1,d0,d1) tensor, got {a.shape}")
+        lnz = C.c_double(0.0)
+        tape = C.c_void_p()
+        self.check(self.lib.tnad_trg_forward(self.h, _p(a), a.shape[0], a.shape[1], int(chi), int(niter), float(tol),
+                                             C.byref(lnz), C.byref(tape) if want_tape else None))
+        return (lnz.value, Tape(self, tape, a.shape)) if want_tape else lnz.value
+
+    def trg_backward(self, tape, dlnZ=1.0):
+        da = np.empty(tape.shape, order="F")
+        self.check(self.lib.tnad_trg_backward(self.h, tape.h, float(dlnZ), _p(da)))
+        return da
+
+    # ---- CTMRG --------------------------------------------------------------------------------------
+    def ctmrg_init_raw(self, bulk, chi):
+        bulk = farray(bulk)
+        D = bulk.shape[0]
+        corner = np.empty((chi, chi), order="F"); edge = np.empty((chi, D, chi), order="F")
+        self.check(self.lib.tnad_ctmrg_init_raw(self.h, _p(bulk), D, int(chi), _p(corner), _p(edge)))
+        return corner, edge
+
+    def ctmrgstep(self, bulk, corner, edge):
+        bulk = farray(bulk)
+        D = bulk.shape[0]
+        chi = np.shape(corner)[0]
+        corner, edge = farray(corner, (chi, chi)), farray(edge, (chi, D, chi))
+        co = np.empty_like(corner, order="F"); eo = np.empty_like(edge, order="F"); vals = np.empty(chi * D)
+        self.check(self.lib.tnad_ctmrgstep(self.h, _p(bulk), D, chi, _p(corner), _p(edge), _p(co), _p(eo),
+                                           vals.ctypes.data_as(c_double_p)))
+        return co, eo, vals
+
+    def ctmrg(self, bulk, corner, edge, tol, maxit, want_tape=False):
+        bulk = farray(bulk)
+        D = bulk.shape[0]
+        chi = np.shape(corner)[0]
+        if bulk.shape != (D, D, D, D):
+            raise DimensionMismatch(f"bulk must be (D,D,D,D), got {bulk.shape}")
+        co = farray(corner, (chi, chi)).copy(order="F"); ed = farray(edge, (chi, D, chi)).copy(order="F")
+        vals = np.empty(chi * D)
+        steps = C.c_int(0)
+        tape = C.c_void_p()
+        self.check(self.lib.tnad_ctmrg(self.h, _p(bulk), D, chi, _p(co), _p(ed), float(tol), int(maxit),
+                                       C.byref(steps), vals.ctypes.data_as(c_double_p),
+                                       C.byref(tape) if want_tape else None))
+        out = (co, ed, vals, steps.value)
+        return out + (Tape(self, tape, (D, chi)),) if want_tape else out
+
+    def ctmrg_backward(self, tape, dcorner, dedge, want_init=False):
+        D, chi = tape.shape
+        dcorner, dedge = farray(dcorner, (chi, chi)), farray(dedge, (chi, D, chi))
+        db = np.empty((D, D, D, D), order="F")
+        dc0 = np.empty((chi, chi), order="F") if want_init else None
+        de0 = np.empty((chi, D, chi), order="F") if want_init else None
+        self.check(self.lib.tnad_ctmrg_backward(self.h, tape.h, _p(dcorner), _p(dedge), _p(db), _p(dc0), _p(de0)))
+        return (db, dc0, de0) if want_init else db
+
+    # ---- energy --------------------------------------------------------------------------------------
+    def expectationvalue(self, h, ap, corner, edge):
+        h, ap = farray(h), farray(ap)
+        s, D, chi = h.shape[0], ap.shape[0], np.shape(corner)[0]
+        corner, edge = farray(corner, (chi, chi)), farray(edge, (chi, D, chi))
+        e = C.c_double(0.0)
+        self.check(self.lib.tnad_expectationvalue(self.h, _p(h), _p(ap), D, s, _p(corner), _p(edge), chi, C.byref(e)))
+        return e.value
+
+    def energy(self, h, A, chi, tol, maxit, grad=False):
+        h, A = farray(h), farray(A)
+        if A.ndim != 5 or not (A.shape[0] == A.shape[1] == A.shape[2] == A.shape[3]):
+            raise DimensionMismatch(f"size of tensor error, should be `(d, d, d, d, s)`, got {A.shape}.")
+        d, s = A.shape[0], A.shape[4]
+        if h.shape != (s, s, s, s):
+            raise DimensionMismatch(f"h must be ({s},{s},{s},{s}), got {h.shape}")
+        e = C.c_double(0.0)
+        steps = C.c_int(0)
+        g = np.empty(A.shape, order="F") if grad else None
+        self.check(self.lib.tnad_energy(self.h, _p(h), _p(A), d, s, int(chi), float(tol), int(maxit), C.byref(e),
+                                        _p(g), C.byref(steps)))
+        self.last_steps = steps.value
+        return (e.value, g) if grad else e.value
+
+    def magnetisation_readout(self, a, m, corner, edge):
+        a, m = farray(a), farray(m)
+        D, chi = a.shape[0], np.shape(corner)[0]
+        corner, edge = farray(corner, (chi, chi)), farray(edge, (chi, D, chi))
+        mag = C.c_double(0.0)
+        self.check(self.lib.tnad_magnetisation_readout(self.h, _p(a), _p(m), D, _p(corner), _p(edge), chi,
+                                                       C.byref(mag)))
+        return mag.value
+
+
+class Tape:
+    """Opaque device-resident record of a forward pass (tnad_tape)."""
+
+    def __init__(self, ctx: Context, h, shape):
+        self.ctx, self.h, self.shape = ctx, h, tuple(shape)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.tnad_tape_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def contract_plan(spec: str, dimsA, dimsB):
+    """Host-only: the GEMM descriptor for a pairwise einsum (used by the CPU tests)."""
+    lib = load_library()
+    da = (C.c_int64 * len(dimsA))(*dimsA)
+    db = (C.c_int64 * len(dimsB))(*dimsB)
+    plan = (C.c_int64 * 128)()
+    rc = lib.tnad_contract_plan(spec.encode(), da, len(dimsA), db, len(dimsB), plan)
+    if rc != 0:
+        raise TnadError(rc, f"contract_plan({spec})")
+    p = list(plan)
+    names = ["am", "ak", "bk", "bn", "cm", "cn", "ab", "bb", "cb"]
+    sets = {}
+    for i, nm in enumerate(names):
+        q = p[8 + 9 * i: 8 + 9 * (i + 1)]
+        nl = q[0]
+        sets[nm] = [(q[1 + l], q[5 + l]) for l in range(nl)]
+    return dict(M=p[0], N=p[1], K=p[2], batch=p[3], a_kfast=p[4], b_kfast=p[5], a_vec=p[6], b_vec=p[7], **sets)

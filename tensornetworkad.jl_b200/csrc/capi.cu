@@ -1,0 +1,381 @@
+// extern "C" surface of libtnad_b200.so (see include/tnad.h).  No exception crosses this boundary.
+#include "drivers.h"
+#include <mutex>
+
+using namespace tnad;
+
+static std::string g_create_error;
+
+#define TNAD_API_BEGIN(ctx)                       \
+  if (!(ctx)) return TNAD_ERR_ARG;                \
+  try {                                           \
+    TNAD_CUDA(cudaSetDevice((ctx)->device));
+
+#define TNAD_API_END(ctx)                                           \
+    return TNAD_OK;                                                 \
+  } catch (const tnad::Error& e) {                                  \
+    (ctx)->err = e.msg;                                             \
+    cudaGetLastError();                                             \
+    return e.code;                                                  \
+  } catch (const std::bad_alloc&) {                                 \
+    (ctx)->err = "host out of memory";                              \
+    return TNAD_ERR_NOMEM;                                          \
+  } catch (const std::exception& e) {                               \
+    (ctx)->err = std::string("internal error: ") + e.what();        \
+    return TNAD_ERR_INTERNAL;                                       \
+  } catch (...) {                                                   \
+    (ctx)->err = "unknown internal error";                          \
+    return TNAD_ERR_INTERNAL;                                       \
+  }
+
+extern "C" {
+
+int tnad_version(void) { return 100; }
+
+int tnad_create(int device, tnad_ctx** out) {
+  if (!out) return TNAD_ERR_ARG;
+  *out = nullptr;
+  tnad_ctx* c = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      fail(TNAD_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                              "); libtnad_b200 has no CPU fallback");
+    TNAD_REQUIRE(device >= 0 && device < ndev, "tnad_create: device index out of range");
+    cudaDeviceProp prop;
+    TNAD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      fail(TNAD_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                              std::to_string(prop.minor) + "; libtnad_b200 is built for sm_100a only");
+    TNAD_CUDA(cudaSetDevice(device));
+    c = new tnad_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    TNAD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TNAD_CUDA(cudaMalloc((void**)&c->scal, SCAL_SLOTS * sizeof(double)));
+    TNAD_CUDA(cudaMalloc((void**)&c->partial, PARTIAL_SLOTS * sizeof(double)));
+    TNAD_CUDA(cudaMallocHost((void**)&c->hpin, HPIN_SLOTS * sizeof(double)));
+    TNAD_CUDA(cudaMemset(c->scal, 0, SCAL_SLOTS * sizeof(double)));
+    // keep freed blocks in the stream-ordered pool: the CTMRG loop re-allocates the same sizes every step
+    cudaMemPool_t pool;
+    TNAD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    TNAD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return TNAD_OK;
+  } catch (const tnad::Error& e) {
+    g_create_error = e.msg;
+    if (c) delete c;
+    return e.code;
+  } catch (...) {
+    g_create_error = "unknown error in tnad_create";
+    if (c) delete c;
+    return TNAD_ERR_INTERNAL;
+  }
+}
+
+int tnad_destroy(tnad_ctx* c) {
+  if (!c) return TNAD_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& s : c->spans) {
+    cudaEventDestroy(s.second.first);
+    cudaEventDestroy(s.second.second);
+  }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  cudaFree(c->scal);
+  cudaFree(c->partial);
+  cudaFreeHost(c->hpin);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return TNAD_OK;
+}
+
+const char* tnad_last_error(tnad_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int tnad_set_pointer_mode(tnad_ctx* c, int mode) {
+  if (!c || (mode != TNAD_POINTER_HOST && mode != TNAD_POINTER_DEVICE)) return TNAD_ERR_ARG;
+  c->pointer_mode = mode;
+  return TNAD_OK;
+}
+
+int tnad_synchronize(tnad_ctx* c) {
+  TNAD_API_BEGIN(c)
+  sync(c);
+  TNAD_API_END(c)
+}
+
+int64_t tnad_launch_count(tnad_ctx* c) { return c ? c->launches : -1; }
+int tnad_reset_launch_count(tnad_ctx* c) {
+  if (!c) return TNAD_ERR_ARG;
+  c->launches = 0;
+  return TNAD_OK;
+}
+
+int tnad_dev_alloc(tnad_ctx* c, int64_t n, double** dptr) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(dptr && n >= 0, "tnad_dev_alloc: bad arguments");
+  TNAD_CUDA(cudaMalloc((void**)dptr, (size_t)(n ? n + 2 : 2) * sizeof(double)));
+  TNAD_API_END(c)
+}
+int tnad_dev_free(tnad_ctx* c, double* dptr) {
+  TNAD_API_BEGIN(c)
+  sync(c);
+  TNAD_CUDA(cudaFree(dptr));
+  TNAD_API_END(c)
+}
+int tnad_dev_upload(tnad_ctx* c, double* dptr, const double* host, int64_t n) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(dptr && host && n >= 0, "tnad_dev_upload: bad arguments");
+  h2d(c, dptr, host, (size_t)n);
+  sync(c);
+  TNAD_API_END(c)
+}
+int tnad_dev_download(tnad_ctx* c, double* host, const double* dptr, int64_t n) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(dptr && host && n >= 0, "tnad_dev_download: bad arguments");
+  TNAD_CUDA(cudaMemcpyAsync(host, dptr, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  sync(c);
+  TNAD_API_END(c)
+}
+
+int tnad_last_timing(tnad_ctx* c, double* ms) {
+  if (!c || !ms) return TNAD_ERR_ARG;
+  for (int i = 0; i < 8; ++i) ms[i] = c->timing[i];
+  return TNAD_OK;
+}
+
+// ---- building blocks --------------------------------------------------------------------------------
+int tnad_contract(tnad_ctx* c, const char* spec, const double* A, const int64_t* dimsA, int rankA, const double* B,
+                  const int64_t* dimsB, int rankB, double alpha, double beta, double* C) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(spec && dimsA && dimsB && rankA >= 0 && rankA <= MAXR && rankB >= 0 && rankB <= MAXR,
+               "tnad_contract: bad arguments");
+  std::vector<int64_t> da(dimsA, dimsA + rankA), db(dimsB, dimsB + rankB);
+  Tens tA = t_in(c, A, da), tB = t_in(c, B, db);
+  std::string s(spec);
+  size_t arrow = s.find("->"), comma = s.find(',');
+  TNAD_REQUIRE(arrow != std::string::npos && comma != std::string::npos, "tnad_contract: bad spec");
+  std::string la, lb, lc;
+  for (char ch : s.substr(0, comma)) if (ch != ' ') la += ch;
+  for (char ch : s.substr(comma + 1, arrow - comma - 1)) if (ch != ' ') lb += ch;
+  for (char ch : s.substr(arrow + 2)) if (ch != ' ') lc += ch;
+  std::vector<int64_t> dc;
+  for (char ch : lc) {
+    size_t ia = la.find(ch), ib = lb.find(ch);
+    TNAD_REQUIRE(ia != std::string::npos || ib != std::string::npos, "tnad_contract: output label not in inputs");
+    dc.push_back(ia != std::string::npos ? da[ia] : db[ib]);
+  }
+  Tens tC;
+  if (beta != 0.0) tC = t_in(c, C, dc);
+  else tC = (c->pointer_mode == TNAD_POINTER_DEVICE) ? t_wrap(C, dc) : t_alloc_v(c, dc);
+  contract(c, spec, tA, tB, tC, alpha, beta);
+  if (c->pointer_mode == TNAD_POINTER_DEVICE) sync(c);
+  else t_out(c, tC, C);
+  TNAD_API_END(c)
+}
+
+int tnad_svd(tnad_ctx* c, const double* A, int m, int n, double* U, double* S, double* V, int* sweeps_out) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(m >= 1 && n >= 1, "tnad_svd: empty matrix");
+  Tens tA = t_in(c, A, {m, n});
+  SvdResult r = svd_jacobi(c, tA, false);
+  t_out(c, r.U, U);
+  t_out(c, r.S, S);
+  t_out(c, r.V, V);
+  if (sweeps_out) *sweeps_out = r.sweeps;
+  TNAD_API_END(c)
+}
+
+int tnad_trg_svd(tnad_ctx* c, const double* t, int d1, int d2, int d3, int d4, int dmax, double tol, double* u,
+                 double* v, int* k_out) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(d1 >= 1 && d2 >= 1 && d3 >= 1 && d4 >= 1 && dmax >= 1 && k_out, "tnad_trg_svd: bad arguments");
+  Tens tt = t_in(c, t, {d1, d2, d3, d4});
+  TrgSplit sp = trg_split(c, tt, dmax, tol);
+  *k_out = (int)sp.k;
+  t_out(c, sp.us, u);
+  Tens vt = t_clone(c, t_perm(sp.vs, {2, 0, 1}));   // (k, d3, d4) as the reference returns it
+  t_out(c, vt, v);
+  TNAD_API_END(c)
+}
+
+int tnad_svd_back(tnad_ctx* c, int m, int n, int k, const double* U, const double* S, const double* V,
+                  const double* dU, const double* dS, const double* dV, double eta, double* dA) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(m >= 1 && n >= 1 && k == std::min(m, n), "tnad_svd_back: k must equal min(m, n)");
+  TNAD_REQUIRE(dU || dS || dV, "tnad_svd_back: all cotangents are nothing");
+  Tens tU = t_in(c, U, {m, k}), tS = t_in(c, S, {k}), tV = t_in(c, V, {n, k});
+  Tens tdU, tdS, tdV;
+  if (dU) tdU = t_in(c, dU, {m, k});
+  if (dS) tdS = t_in(c, dS, {k});
+  if (dV) tdV = t_in(c, dV, {n, k});
+  Tens r = svd_back_dev(c, tU, tS, tV, dU ? &tdU : nullptr, dS ? &tdS : nullptr, dV ? &tdV : nullptr, k, eta);
+  t_out(c, r, dA);
+  TNAD_API_END(c)
+}
+
+// ---- TRG ----------------------------------------------------------------------------------------------
+int tnad_trg_forward(tnad_ctx* c, const double* a, int d0, int d1, int chi, int niter, double tol, double* lnZ,
+                     tnad_tape** tape) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(lnZ && d0 >= 1 && d1 >= 1, "tnad_trg_forward: bad arguments");
+  timing_begin(c);
+  Tens ta = t_in(c, a, {d0, d1, d0, d1});
+  tnad_tape* tp = nullptr;
+  if (tape) {
+    tp = new tnad_tape();
+    tp->ctx = c;
+    tp->kind = 1;
+  }
+  try {
+    Span sp(c, 0);
+    *lnZ = trg_forward(c, ta, chi, niter, tol, tp ? &tp->trg : nullptr);
+  } catch (...) {
+    delete tp;
+    throw;
+  }
+  timing_end(c);
+  if (tape) *tape = tp;
+  TNAD_API_END(c)
+}
+
+int tnad_trg_backward(tnad_ctx* c, tnad_tape* tape, double dlnZ, double* da) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(tape && tape->kind == 1 && tape->ctx == c && da, "tnad_trg_backward: not a TRG tape of this context");
+  timing_begin(c);
+  Tens g;
+  {
+    Span sp(c, 0);
+    g = trg_backward(c, tape->trg, dlnZ);
+  }
+  t_out(c, g, da);
+  timing_end(c);
+  TNAD_API_END(c)
+}
+
+int tnad_tape_free(tnad_tape* tape) {
+  if (!tape) return TNAD_OK;
+  if (tape->ctx) cudaSetDevice(tape->ctx->device);
+  delete tape;
+  return TNAD_OK;
+}
+
+// ---- CTMRG --------------------------------------------------------------------------------------------
+int tnad_ctmrg_init_raw(tnad_ctx* c, const double* bulk, int D, int chi, double* corner, double* edge) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && chi >= 1, "tnad_ctmrg_init_raw: bad arguments");
+  Tens b = t_in(c, bulk, {D, D, D, D});
+  Tens co = t_alloc(c, {chi, chi}), ed = t_alloc(c, {chi, D, chi});
+  init_raw(c, b, co, ed);
+  t_out(c, co, corner);
+  t_out(c, ed, edge);
+  TNAD_API_END(c)
+}
+
+int tnad_ctmrgstep(tnad_ctx* c, const double* bulk, int D, int chi, const double* corner_in, const double* edge_in,
+                   double* corner_out, double* edge_out, double* vals) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && chi >= 1, "tnad_ctmrgstep: bad arguments");
+  Tens b = t_in(c, bulk, {D, D, D, D}), co = t_in(c, corner_in, {chi, chi}), ed = t_in(c, edge_in, {chi, D, chi});
+  Tens cn, en;
+  std::vector<double> v;
+  ctmrg_step(c, b, co, ed, cn, en, v, nullptr);
+  t_out(c, cn, corner_out);
+  t_out(c, en, edge_out);
+  if (vals) memcpy(vals, v.data(), v.size() * sizeof(double));
+  TNAD_API_END(c)
+}
+
+int tnad_ctmrg(tnad_ctx* c, const double* bulk, int D, int chi, double* corner, double* edge, double tol, int maxit,
+               int* steps_done, double* vals, tnad_tape** tape) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && chi >= 1 && maxit >= 0, "tnad_ctmrg: bad arguments");
+  timing_begin(c);
+  Tens b = t_in(c, bulk, {D, D, D, D});
+  // the environment is in/out: work on private copies so a device-mode caller's buffers are only written at the end
+  Tens co = t_clone(c, t_in(c, corner, {chi, chi})), ed = t_clone(c, t_in(c, edge, {chi, D, chi}));
+  if (c->pointer_mode == TNAD_POINTER_DEVICE) b = t_clone(c, b);
+  tnad_tape* tp = nullptr;
+  if (tape) {
+    tp = new tnad_tape();
+    tp->ctx = c;
+    tp->kind = 2;
+  }
+  std::vector<double> v;
+  int ns = 0;
+  try {
+    Span sp(c, 0);
+    ns = ctmrg_loop(c, b, co, ed, tol, maxit, v, tp ? &tp->ctmrg : nullptr);
+  } catch (...) {
+    delete tp;
+    throw;
+  }
+  t_out(c, co, corner);
+  t_out(c, ed, edge);
+  if (steps_done) *steps_done = ns;
+  if (vals) memcpy(vals, v.data(), v.size() * sizeof(double));
+  timing_end(c);
+  if (tape) *tape = tp;
+  TNAD_API_END(c)
+}
+
+int tnad_ctmrg_backward(tnad_ctx* c, tnad_tape* tape, const double* dcorner, const double* dedge, double* dbulk,
+                        double* dcorner0, double* dedge0) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(tape && tape->kind == 2 && tape->ctx == c && dbulk, "tnad_ctmrg_backward: not a CTMRG tape of this context");
+  timing_begin(c);
+  const int64_t D = tape->ctmrg.D, chi = tape->ctmrg.chi;
+  Tens cb = t_in(c, dcorner, {chi, chi}), eb = t_in(c, dedge, {chi, D, chi});
+  Tens bb, cb0, eb0;
+  {
+    Span sp(c, 0);
+    Span sp3(c, 3);
+    ctmrg_backward(c, tape->ctmrg, cb, eb, bb, cb0, eb0, 1e-40);
+  }
+  t_out(c, bb, dbulk);
+  if (dcorner0) t_out(c, cb0, dcorner0);
+  if (dedge0) t_out(c, eb0, dedge0);
+  timing_end(c);
+  TNAD_API_END(c)
+}
+
+// ---- energy -------------------------------------------------------------------------------------------
+int tnad_expectationvalue(tnad_ctx* c, const double* h, const double* ap, int D, int s, const double* corner,
+                          const double* edge, int chi, double* e) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(e && D >= 1 && s >= 1 && chi >= 1, "tnad_expectationvalue: bad arguments");
+  Tens th = t_in(c, h, {s, s, s, s}), tap = t_in(c, ap, {D, D, D, D, s, s});
+  Tens co = t_in(c, corner, {chi, chi}), ed = t_in(c, edge, {chi, D, chi});
+  *e = expectationvalue(c, th, tap, co, ed, nullptr);
+  TNAD_API_END(c)
+}
+
+int tnad_energy(tnad_ctx* c, const double* h, const double* A, int d, int s, int chi, double tol, int maxit,
+                double* e, double* gradA, int* steps_done) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(e && d >= 1 && s >= 1, "tnad_energy: bad arguments");
+  timing_begin(c);
+  Tens th = t_in(c, h, {s, s, s, s}), tA = t_in(c, A, {d, d, d, d, s});
+  Tens g;
+  {
+    Span sp(c, 0);
+    *e = energy(c, th, tA, chi, tol, maxit, gradA ? &g : nullptr, steps_done);
+  }
+  if (gradA) t_out(c, g, gradA);
+  timing_end(c);
+  TNAD_API_END(c)
+}
+
+int tnad_magnetisation_readout(tnad_ctx* c, const double* a, const double* m, int D, const double* corner,
+                               const double* edge, int chi, double* mag) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(mag && D >= 1 && chi >= 1, "tnad_magnetisation_readout: bad arguments");
+  Tens ta = t_in(c, a, {D, D, D, D}), tm = t_in(c, m, {D, D, D, D});
+  Tens co = t_in(c, corner, {chi, chi}), ed = t_in(c, edge, {chi, D, chi});
+  *mag = magnetisation_readout(c, ta, tm, co, ed);
+  TNAD_API_END(c)
+}
+
+}  // extern "C"

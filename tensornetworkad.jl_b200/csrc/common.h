@@ -1,0 +1,211 @@
+// Internal header of libtnad_b200: context, device tensors, error plumbing, kernel prototypes.
+// Nothing here is part of the C ABI (see include/tnad.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <memory>
+#include <string>
+#include <vector>
+#include <initializer_list>
+#include "../../include/tnad.h"
+
+namespace tnad {
+
+struct Error {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] inline void fail(int code, const std::string& msg) { throw Error{code, msg}; }
+
+#define TNAD_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::tnad::fail(_e == cudaErrorMemoryAllocation ? TNAD_ERR_NOMEM : TNAD_ERR_CUDA,            \
+                   std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                       std::to_string(__LINE__) + ")");                                         \
+    }                                                                                           \
+  } while (0)
+
+#define TNAD_REQUIRE(cond, msg)                                  \
+  do {                                                           \
+    if (!(cond)) ::tnad::fail(TNAD_ERR_ARG, std::string(msg));   \
+  } while (0)
+
+}  // namespace tnad
+
+struct tnad_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int pointer_mode = TNAD_POINTER_HOST;
+  int64_t launches = 0;
+  double* scal = nullptr;      // device scalar scratch (SCAL_SLOTS doubles)
+  double* partial = nullptr;   // reduction partials (PARTIAL_SLOTS doubles)
+  double* hpin = nullptr;      // pinned host staging (HPIN_SLOTS doubles)
+  int num_sms = 148;
+  double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // accumulators for the timing breakdown (host wall clock around synchronised phases is not
+  // used; phases are bracketed by events and summed at the end of a call)
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+namespace tnad {
+
+constexpr int SCAL_SLOTS = 1024;
+constexpr int PARTIAL_SLOTS = 4096;
+constexpr int HPIN_SLOTS = 1 << 16;
+
+// --------------------------------------------------------------------------------------------
+// device buffers and tensors
+// --------------------------------------------------------------------------------------------
+struct DBuf {
+  tnad_ctx* c;
+  double* p;
+  size_t n;
+  DBuf(tnad_ctx* c_, size_t n_) : c(c_), p(nullptr), n(n_) {
+    TNAD_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(double), c->stream));
+  }
+  ~DBuf() {
+    if (p) cudaFreeAsync(p, c->stream);
+  }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+};
+
+constexpr int MAXR = 10;
+
+// A strided view of doubles on the device. dim/str follow the Julia index order (dim[0] is the
+// first Julia index); a freshly allocated tensor is column-major contiguous.
+struct Tens {
+  double* p = nullptr;
+  int rank = 0;
+  int64_t dim[MAXR] = {0};
+  int64_t str[MAXR] = {0};
+  std::shared_ptr<DBuf> own;
+
+  int64_t numel() const {
+    int64_t n = 1;
+    for (int i = 0; i < rank; ++i) n *= dim[i];
+    return n;
+  }
+  bool contiguous() const {
+    int64_t s = 1;
+    for (int i = 0; i < rank; ++i) {
+      if (dim[i] != 1 && str[i] != s) return false;
+      s *= dim[i];
+    }
+    return true;
+  }
+};
+
+Tens t_alloc(tnad_ctx* c, std::initializer_list<int64_t> dims, bool zero = false);
+Tens t_alloc_v(tnad_ctx* c, const std::vector<int64_t>& dims, bool zero = false);
+Tens t_wrap(double* p, const std::vector<int64_t>& dims);                       // non-owning, contiguous
+Tens t_reshape(const Tens& t, std::initializer_list<int64_t> dims);             // contiguous only
+Tens t_perm(const Tens& t, std::initializer_list<int> perm);                    // view, no data movement
+Tens t_slice_last(const Tens& t, int64_t start, int64_t count);                 // slice of last index
+Tens t_in(tnad_ctx* c, const double* user, const std::vector<int64_t>& dims);   // host->upload / device->wrap
+void t_out(tnad_ctx* c, const Tens& t, double* user);                           // contiguous tensor -> user
+Tens t_clone(tnad_ctx* c, const Tens& t);                                       // contiguous copy
+void t_zero(tnad_ctx* c, Tens& t);
+void sync(tnad_ctx* c);
+void d2h(tnad_ctx* c, double* host, const double* dev, size_t n);               // synchronous
+void h2d(tnad_ctx* c, double* dev, const double* host, size_t n);
+
+// timing spans (CUDA events on the ctx stream)
+struct Span {
+  tnad_ctx* c;
+  int key;
+  cudaEvent_t a, b;
+  Span(tnad_ctx* c, int key);
+  ~Span();
+};
+void timing_begin(tnad_ctx* c);
+void timing_end(tnad_ctx* c);   // synchronises and sums the spans into c->timing
+
+// --------------------------------------------------------------------------------------------
+// GEMM with multi-level strides ("permute-on-load")
+// --------------------------------------------------------------------------------------------
+constexpr int MAXL = 4;
+struct LvlSet {
+  int nl;
+  int n[MAXL];
+  long long s[MAXL];
+};
+struct GemmDesc {
+  int M, N, K, batch;
+  LvlSet am, ak, bk, bn, cm, cn, ab, bb, cb;
+  const double* A;
+  const double* B;
+  double* C;
+  double alpha, beta;
+  int a_kfast, b_kfast, a_vec, b_vec;
+};
+void gemm_run(tnad_ctx* c, const GemmDesc& d);
+
+// einsum pairwise contraction C[..] = alpha * sum A[..] B[..] + beta C[..]
+GemmDesc contract_plan(const char* spec, const Tens& A, const Tens& B, const Tens& C);
+void contract(tnad_ctx* c, const char* spec, const Tens& A, const Tens& B, Tens& C, double alpha = 1.0,
+              double beta = 0.0);
+// allocate the output (column-major in the label order of the spec's right-hand side) and contract
+Tens contract_new(tnad_ctx* c, const char* spec, const Tens& A, const Tens& B, double alpha = 1.0);
+
+// --------------------------------------------------------------------------------------------
+// elementwise / reduction kernels (elementwise.cu)
+// --------------------------------------------------------------------------------------------
+// out = alpha * in + beta * out over a common index space given by out.dim; `in` must have the same
+// rank and dims (use t_perm to express permutations).
+void tcopy(tnad_ctx* c, const Tens& in, Tens& out, double alpha = 1.0, double beta = 0.0);
+enum RedOp { RED_SUMSQ = 0, RED_DOT = 1, RED_ABSMAX = 2, RED_SUM = 3 };
+// contiguous tensors; result -> device scalar *res
+void reduce(tnad_ctx* c, RedOp op, const Tens& x, const Tens* y, double* res);
+enum ScaleMode { SC_INV = 0, SC_INVSQRT = 1, SC_MUL = 2 };
+// out = in * f(*scalar)   (INV: 1/s, INVSQRT: 1/sqrt(s), MUL: s); contiguous, may alias
+void scale_dev(tnad_ctx* c, const Tens& in, Tens& out, const double* scalar, ScaleMode mode);
+// xbar = ybar / sqrt(ss) - dot * x / sqrt(ss)^3  (norm pullback, autodiff.jl:23-29); ss = sum x^2
+void norm_back(tnad_ctx* c, const Tens& ybar, const Tens& x, const double* ss, const double* dot, Tens& xbar);
+void trace_ijij(tnad_ctx* c, const Tens& a, double* res);
+// out[:, j] = in[:, j] * sqrt(S[j]) for j < k    (m x k, contiguous columns with given lds)
+void colscale_sqrt(tnad_ctx* c, const double* in, int64_t ldin, const double* S, double* out, int64_t ldout,
+                   int64_t m, int64_t k);
+void set_identity(tnad_ctx* c, double* p, int64_t ld, int64_t n);
+void init_raw(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge);
+void ipeps_symmetrize(tnad_ctx* c, const Tens& A, Tens& xsum, Tens& out, double* ss);
+void ipeps_symmetrize_back(tnad_ctx* c, const Tens& ybar, const Tens& xsum, const double* ss, Tens& Abar);
+void double_layer(tnad_ctx* c, const Tens& A, Tens& ap, Tens& a);
+void double_layer_back(tnad_ctx* c, const Tens& A, const Tens& apbar, const Tens& abar, Tens& Abar);
+// svd_back core: panels of R = (J+J')S + S(K+K') + diag(dS)  (trg.jl:79-93) restricted to the
+// first k rows (Rrow, k x n) and the first k columns below row k (Rcol, n x k, rows < k zeroed).
+void svdback_panels(tnad_ctx* c, int64_t n, int64_t k, const double* S, const double* G1, const double* G2,
+                    const double* dS, double eta, double* Rrow, double* Rcol);
+// x[:, j] *= S[j]/(S[j]^2+eta)
+void colscale_sinv(tnad_ctx* c, double* x, int64_t ld, int64_t m, int64_t k, const double* S, double eta);
+// TRG: dS[j] = (sum_i U[i,j] du[i,j] + sum_i V[i,j] dvt[j,i]) / (2 sqrt(S[j])), dU = du*sqrt(S), dV = (sqrt(S) dvt)'
+void trg_factor_back(tnad_ctx* c, int64_t m, int64_t n, int64_t k, const double* U, int64_t ldu, const double* V,
+                     int64_t ldv, const double* S, const double* du, const double* dvt, double* dUk, double* dVk,
+                     double* dS);
+void add_diag_trace_back(tnad_ctx* c, Tens& abar, double w);   // abar[i,j,i,j] += w
+void trg_maxval_back(tnad_ctx* c, const Tens& da, const Tens& a_in, double maxval, double coef, Tens& da_in);
+void fill(tnad_ctx* c, double* p, int64_t n, double v);
+
+// --------------------------------------------------------------------------------------------
+// Jacobi SVD (jacobi.cu)
+// --------------------------------------------------------------------------------------------
+struct SvdResult {
+  Tens U;   // m x k
+  Tens S;   // k
+  Tens V;   // n x k
+  std::vector<double> s_host;
+  int sweeps = 0;
+};
+// A: any rank-2 strided view (m x n). If sym_add_transpose, the matrix decomposed is A + A^T (m == n).
+SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false);
+
+}  // namespace tnad

@@ -1,0 +1,175 @@
+// Device tensor plumbing: allocation (stream-ordered pool), views, host<->device staging, timing spans.
+#include "common.h"
+
+namespace tnad {
+
+Tens t_alloc_v(tnad_ctx* c, const std::vector<int64_t>& dims, bool zero) {
+  TNAD_REQUIRE((int)dims.size() <= MAXR, "tensor rank too large");
+  Tens t;
+  t.rank = (int)dims.size();
+  int64_t s = 1;
+  for (int i = 0; i < t.rank; ++i) {
+    TNAD_REQUIRE(dims[i] >= 0, "negative dimension");
+    t.dim[i] = dims[i];
+    t.str[i] = s;
+    s *= dims[i];
+  }
+  // pad by one double so 16-byte vector accesses on an even-sized prefix never run off the end
+  t.own = std::make_shared<DBuf>(c, (size_t)s + 2);
+  t.p = t.own->p;
+  if (zero) TNAD_CUDA(cudaMemsetAsync(t.p, 0, (size_t)(s + 2) * sizeof(double), c->stream));
+  return t;
+}
+
+Tens t_alloc(tnad_ctx* c, std::initializer_list<int64_t> dims, bool zero) {
+  return t_alloc_v(c, std::vector<int64_t>(dims), zero);
+}
+
+Tens t_wrap(double* p, const std::vector<int64_t>& dims) {
+  Tens t;
+  t.rank = (int)dims.size();
+  int64_t s = 1;
+  for (int i = 0; i < t.rank; ++i) {
+    t.dim[i] = dims[i];
+    t.str[i] = s;
+    s *= dims[i];
+  }
+  t.p = p;
+  return t;
+}
+
+Tens t_reshape(const Tens& t, std::initializer_list<int64_t> dims) {
+  TNAD_REQUIRE(t.contiguous(), "reshape of a non-contiguous view");
+  Tens r = t_wrap(t.p, std::vector<int64_t>(dims));
+  TNAD_REQUIRE(r.numel() == t.numel(), "reshape: element count mismatch");
+  r.own = t.own;
+  return r;
+}
+
+Tens t_perm(const Tens& t, std::initializer_list<int> perm) {
+  TNAD_REQUIRE((int)perm.size() == t.rank, "perm: rank mismatch");
+  Tens r;
+  r.p = t.p;
+  r.rank = t.rank;
+  r.own = t.own;
+  int i = 0;
+  for (int p : perm) {
+    r.dim[i] = t.dim[p];
+    r.str[i] = t.str[p];
+    ++i;
+  }
+  return r;
+}
+
+Tens t_slice_last(const Tens& t, int64_t start, int64_t count) {
+  Tens r = t;
+  int l = t.rank - 1;
+  TNAD_REQUIRE(l >= 0 && start >= 0 && start + count <= t.dim[l], "slice out of range");
+  r.p = t.p + start * t.str[l];
+  r.dim[l] = count;
+  return r;
+}
+
+void sync(tnad_ctx* c) { TNAD_CUDA(cudaStreamSynchronize(c->stream)); }
+
+void d2h(tnad_ctx* c, double* host, const double* dev, size_t n) {
+  if (n == 0) return;
+  if (n <= (size_t)HPIN_SLOTS) {
+    TNAD_CUDA(cudaMemcpyAsync(c->hpin, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    sync(c);
+    memcpy(host, c->hpin, n * sizeof(double));
+  } else {
+    TNAD_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    sync(c);
+  }
+}
+
+void h2d(tnad_ctx* c, double* dev, const double* host, size_t n) {
+  if (n == 0) return;
+  // pageable source: cudaMemcpyAsync stages it before returning, so the caller's buffer may be reused
+  TNAD_CUDA(cudaMemcpyAsync(dev, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+}
+
+Tens t_in(tnad_ctx* c, const double* user, const std::vector<int64_t>& dims) {
+  TNAD_REQUIRE(user != nullptr, "null input array");
+  if (c->pointer_mode == TNAD_POINTER_DEVICE) return t_wrap(const_cast<double*>(user), dims);
+  Tens t = t_alloc_v(c, dims);
+  h2d(c, t.p, user, (size_t)t.numel());
+  return t;
+}
+
+void t_out(tnad_ctx* c, const Tens& t, double* user) {
+  TNAD_REQUIRE(user != nullptr, "null output array");
+  Tens src = t;
+  if (!t.contiguous()) src = t_clone(c, t);
+  size_t n = (size_t)src.numel();
+  if (c->pointer_mode == TNAD_POINTER_DEVICE) {
+    if (n) TNAD_CUDA(cudaMemcpyAsync(user, src.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    sync(c);
+  } else {
+    if (n) TNAD_CUDA(cudaMemcpyAsync(user, src.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    sync(c);
+  }
+}
+
+Tens t_clone(tnad_ctx* c, const Tens& t) {
+  std::vector<int64_t> dims(t.dim, t.dim + t.rank);
+  Tens r = t_alloc_v(c, dims);
+  if (t.contiguous()) {
+    if (t.numel())
+      TNAD_CUDA(cudaMemcpyAsync(r.p, t.p, (size_t)t.numel() * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    tcopy(c, t, r, 1.0, 0.0);
+  }
+  return r;
+}
+
+void t_zero(tnad_ctx* c, Tens& t) {
+  TNAD_REQUIRE(t.contiguous(), "t_zero on a view");
+  if (t.numel()) TNAD_CUDA(cudaMemsetAsync(t.p, 0, (size_t)t.numel() * sizeof(double), c->stream));
+}
+
+// ---- timing --------------------------------------------------------------------------------
+static cudaEvent_t get_event(tnad_ctx* c) {
+  if (!c->event_pool.empty()) {
+    cudaEvent_t e = c->event_pool.back();
+    c->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  TNAD_CUDA(cudaEventCreate(&e));
+  return e;
+}
+
+Span::Span(tnad_ctx* c_, int key_) : c(c_), key(key_) {
+  a = get_event(c);
+  b = get_event(c);
+  cudaEventRecord(a, c->stream);
+}
+Span::~Span() {
+  cudaEventRecord(b, c->stream);
+  c->spans.push_back({key, {a, b}});
+}
+
+void timing_begin(tnad_ctx* c) {
+  for (auto& s : c->spans) {
+    c->event_pool.push_back(s.second.first);
+    c->event_pool.push_back(s.second.second);
+  }
+  c->spans.clear();
+  for (int i = 0; i < 8; ++i) c->timing[i] = 0.0;
+}
+
+void timing_end(tnad_ctx* c) {
+  cudaStreamSynchronize(c->stream);
+  for (auto& s : c->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.second.first, s.second.second) == cudaSuccess && s.first >= 0 && s.first < 8)
+      c->timing[s.first] += ms;
+    c->event_pool.push_back(s.second.first);
+    c->event_pool.push_back(s.second.second);
+  }
+  c->spans.clear();
+}
+
+}  // namespace tnad
