@@ -203,9 +203,11 @@ struct SvdResult {
   Tens S;   // k
   Tens V;   // n x k
   std::vector<double> s_host;
+  double null_thr = 0.0;   // singular values <= null_thr are numerically null (their U columns are a completion)
   int sweeps = 0;
 };
 // A: any rank-2 strided view (m x n). If sym_add_transpose, the matrix decomposed is A + A^T (m == n).
-SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false);
+// V0 (optional, n x n orthogonal): warm start for square inputs.
+SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false, const Tens* V0 = nullptr);
 
 }  // namespace tnad

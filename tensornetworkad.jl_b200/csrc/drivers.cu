@@ -5,6 +5,7 @@
 // `tp`-free association documented in DESIGN.md and mirrored one-to-one in oracle/tnad_oracle.py.
 #include "drivers.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace tnad {
 
@@ -67,6 +68,25 @@ TrgSplit trg_split(tnad_ctx* c, const Tens& t4, int64_t dmax, double tol) {
   }
   const int64_t m = t4.dim[0] * t4.dim[1], n = t4.dim[2] * t4.dim[3];
   sp.k = trg_rank_rule(sp.svd.s_host, dmax, tol);
+  // The rank rule keeps one singular value <= tol (trg.jl:37).  For an exactly rank-deficient input that
+  // triplet is numerically null: sqrt(s) is not differentiable at 0 and the reference's result does not
+  // depend on it (it only stays finite there because LAPACK's noise is non-zero).  Treat such values as
+  // exact zeros: the factor columns vanish and so do their cotangents (dS = dsqrt/(2 sqrt(s)) := 0).
+  {
+    std::vector<double> seff = sp.svd.s_host;
+    bool any = false;
+    for (auto& x : seff)
+      if (x <= sp.svd.null_thr) {
+        x = 0.0;
+        any = true;
+      }
+    if (any) {
+      Tens S2 = t_alloc(c, {(int64_t)seff.size()});
+      h2d(c, S2.p, seff.data(), seff.size());
+      sync(c);
+      sp.svd.S = S2;
+    }
+  }
   Tens us = t_alloc(c, {m, sp.k}), vs = t_alloc(c, {n, sp.k});
   colscale_sqrt(c, sp.svd.U.p, m, sp.svd.S.p, us.p, m, m, sp.k);
   colscale_sqrt(c, sp.svd.V.p, n, sp.svd.S.p, vs.p, n, n, sp.k);
@@ -172,7 +192,7 @@ Tens trg_backward(tnad_ctx* c, TrgTape& tape, double dlnZ) {
 // CTMRG
 // =====================================================================================================
 void ctmrg_step(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& edge, Tens& corner_out,
-                Tens& edge_out, std::vector<double>& vals_host, CtmrgStepRec* rec) {
+                Tens& edge_out, std::vector<double>& vals_host, CtmrgStepRec* rec, Tens* Vwarm) {
   const int64_t D = bulk.dim[0], chi = corner.dim[0], n = chi * D;
   Tens X1, X2, cp;
   {
@@ -186,7 +206,9 @@ void ctmrg_step(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& e
   SvdResult svd;
   {
     Span s(c, 1);
-    svd = svd_jacobi(c, CP, true);   // svd(cpmat + cpmat')   (ctmrg.jl:134-136)
+    // svd(cpmat + cpmat') (ctmrg.jl:134-136); warm-started from the previous step's right vectors
+    svd = svd_jacobi(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);
+    if (Vwarm) *Vwarm = svd.V;
   }
   Tens Z = t_slice_last(svd.U, 0, chi);          // u[:, 1:chi]
   Tens z = t_reshape(Z, {chi, D, chi});           // (ctmrg.jl:137)
@@ -245,6 +267,9 @@ int ctmrg_loop(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge, double t
   const size_t n = (size_t)(chi * D);
   std::vector<double> oldvals(n, INFINITY);
   vals.assign(n, INFINITY);
+  const char* wenv = getenv("TNAD_WARMSTART");
+  const bool warm = !(wenv && wenv[0] == '0');
+  Tens Vwarm;
   long long counter = -1;   // ctmrg.jl:114
   int nsteps = 0;
   for (;;) {
@@ -262,7 +287,7 @@ int ctmrg_loop(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge, double t
     oldvals = vals;
     Tens cn, en;
     CtmrgStepRec rec;
-    ctmrg_step(c, bulk, corner, edge, cn, en, vals, tape ? &rec : nullptr);
+    ctmrg_step(c, bulk, corner, edge, cn, en, vals, tape ? &rec : nullptr, warm ? &Vwarm : nullptr);
     if (tape) tape->steps.push_back(rec);
     corner = cn;
     edge = en;

@@ -50,7 +50,7 @@ struct CtmrgTape {
 };
 // one step (ctmrg.jl:126-153); vals_host gets s ./ s[1]
 void ctmrg_step(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& edge, Tens& corner_out,
-                Tens& edge_out, std::vector<double>& vals_host, CtmrgStepRec* rec);
+                Tens& edge_out, std::vector<double>& vals_host, CtmrgStepRec* rec, Tens* Vwarm = nullptr);
 // the fixed-point loop (ctmrg.jl:110-117 + fixedpoint.jl); returns the number of steps executed
 int ctmrg_loop(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge, double tol, int maxit,
                std::vector<double>& vals_host, CtmrgTape* tape);

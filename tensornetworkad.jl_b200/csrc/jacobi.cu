@@ -126,17 +126,19 @@ __global__ void __launch_bounds__(256) k_jacobi_gram(const double* __restrict__ 
 
 // ---- 2. 64x64 symmetric eigenproblem in shared memory -------------------------------------------
 __global__ void __launch_bounds__(512) k_jacobi_eig(const double* __restrict__ Hpart, int nsplit, double tol,
-                                                    int max_inner, double* __restrict__ Wbuf, int* __restrict__ skip,
+                                                    int max_inner, const double* __restrict__ fro2, double nullfac,
+                                                    int p, int round, int nreal, double* __restrict__ Wbuf, int* __restrict__ skip,
                                                     unsigned long long* __restrict__ offmax_bits) {
   extern __shared__ __align__(16) double esm[];
   double* H = esm;
   double* W = H + JP * HLD;
-  double* rc = W + JP * HLD;
-  double* rs = rc + JB;
-  double* red = rs + JB;
-  int* rp = reinterpret_cast<int*>(red + 16);
-  int* rq = rp + JB;
+  double* red = W + JP * HLD;
+  double* dsort = red + 16;
+  int* perm = reinterpret_cast<int*>(dsort + JP);
   const int pair = blockIdx.x, tid = threadIdx.x;
+  // columns whose squared norm is below thr2 = nullfac * |A|_F^2 are numerically null: they lie in
+  // the span of the other columns up to rounding, so their cosines never converge; freeze them.
+  const double thr2 = nullfac * (*fro2);
   const double* hp = Hpart + (long long)pair * nsplit * (JP * JP);
   for (int idx = tid; idx < JP * JP; idx += 512) {
     double h = 0.0;
@@ -146,14 +148,13 @@ __global__ void __launch_bounds__(512) k_jacobi_eig(const double* __restrict__ H
     W[r * HLD + c] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
-  // largest cosine between distinct columns
+  // largest cosine between distinct non-null columns
   double off = 0.0;
   for (int idx = tid; idx < JP * JP; idx += 512) {
     const int r = idx % JP, c = idx / JP;
     if (r < c) {
-      const double den = sqrt(H[r * HLD + r] * H[c * HLD + c]);
-      const double num = fabs(H[r * HLD + c]);
-      if (num > 0.0) off = fmax(off, den > 0.0 ? num / den : 1.0);
+      const double hr = H[r * HLD + r], hc = H[c * HLD + c];
+      if (hr > thr2 && hc > thr2) off = fmax(off, fabs(H[r * HLD + c]) / sqrt(hr * hc));
     }
   }
 #pragma unroll
@@ -170,66 +171,94 @@ __global__ void __launch_bounds__(512) k_jacobi_eig(const double* __restrict__ H
   __syncthreads();
   if (red[0] <= tol) return;
 
+  // Cyclic two-sided Jacobi, 32 disjoint rotations per step.  A half-warp owns one rotation: its 16
+  // lanes each compute the (identical) rotation parameters and apply them to 4 rows / columns.
+  const int kp = tid >> 4, l16 = tid & 15;
+  const double tol2 = tol * tol;
   for (int sw = 0; sw < max_inner; ++sw) {
     int rotated = 0;
     for (int step = 0; step < JP - 1; ++step) {
-      if (tid < JB) {
-        int p_, q_;
-        rr_pair(JP, step, tid, p_, q_);
-        const double app = H[p_ * HLD + p_], aqq = H[q_ * HLD + q_], apq = H[p_ * HLD + q_];
-        double c = 1.0, s = 0.0;
-        if (fabs(apq) > tol * sqrt(app * aqq)) {
-          const double zeta = (aqq - app) / (2.0 * apq);
-          const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + tt * tt);
-          s = c * tt;
-          rotated = 1;
-        }
-        rc[tid] = c;
-        rs[tid] = s;
-        rp[tid] = p_;
-        rq[tid] = q_;
-      }
-      __syncthreads();
-      // column rotations of H and W:  x_p' = c x_p - s x_q ; x_q' = s x_p + c x_q
+      int p_, q_;
+      rr_pair(JP, step, kp, p_, q_);
+      const double app = H[p_ * HLD + p_], aqq = H[q_ * HLD + q_], apq = H[p_ * HLD + q_];
+      __syncwarp();   // all lanes of the pair have read the pivot entries before anyone rotates them
+      const bool rot = app > thr2 && aqq > thr2 && apq * apq > tol2 * app * aqq;
+      double c = 1.0, s = 0.0;
+      if (rot) {
+        // t = sign(tau) 2 apq / (|tau| + sqrt(tau^2 + 4 apq^2)), tau = aqq - app; c = 1/sqrt(1+t^2); s = c t
+        const double tau = aqq - app;
+        const double w = tau * tau + 4.0 * apq * apq;
+        const double d = fabs(tau) + w * rsqrt(w);
+        const double rd = rsqrt(d);
+        const double tt = copysign(2.0 * apq * rd * rd, tau * apq);
+        c = rsqrt(1.0 + tt * tt);
+        s = c * tt;
+        rotated = 1;
 #pragma unroll
-      for (int it = 0; it < (2 * JB * JP) / 512; ++it) {
-        const int item = tid + it * 512;
-        const int mat = item / (JB * JP), rem = item % (JB * JP);
-        const int kp = rem / JP, i = rem % JP;
-        const double s = rs[kp];
-        if (s != 0.0) {
-          const double c = rc[kp];
-          double* Mx = mat ? W : H;
-          const int p_ = rp[kp], q_ = rq[kp];
-          const double xp = Mx[i * HLD + p_], xq = Mx[i * HLD + q_];
-          Mx[i * HLD + p_] = c * xp - s * xq;
-          Mx[i * HLD + q_] = s * xp + c * xq;
+        for (int r = 0; r < JP / 16; ++r) {
+          const int i = l16 + 16 * r;
+          const double hp = H[i * HLD + p_], hq = H[i * HLD + q_];
+          H[i * HLD + p_] = c * hp - s * hq;
+          H[i * HLD + q_] = s * hp + c * hq;
+          const double wp = W[i * HLD + p_], wq = W[i * HLD + q_];
+          W[i * HLD + p_] = c * wp - s * wq;
+          W[i * HLD + q_] = s * wp + c * wq;
         }
       }
       __syncthreads();
-      // row rotations of H
+      if (rot) {
 #pragma unroll
-      for (int it = 0; it < (JB * JP) / 512; ++it) {
-        const int item = tid + it * 512;
-        const int kp = item / JP, j = item % JP;
-        const double s = rs[kp];
-        if (s != 0.0) {
-          const double c = rc[kp];
-          const int p_ = rp[kp], q_ = rq[kp];
-          const double xp = H[p_ * HLD + j], xq = H[q_ * HLD + j];
-          H[p_ * HLD + j] = c * xp - s * xq;
-          H[q_ * HLD + j] = s * xp + c * xq;
+        for (int r = 0; r < JP / 16; ++r) {
+          const int j = l16 + 16 * r;
+          const double hp = H[p_ * HLD + j], hq = H[q_ * HLD + j];
+          H[p_ * HLD + j] = c * hp - s * hq;
+          H[q_ * HLD + j] = s * hp + c * hq;
         }
       }
       __syncthreads();
     }
     if (!__syncthreads_or(rotated)) break;
   }
+  if (tid < JP) {
+    // sort key: squared column norm; padding columns (global index >= nreal, exactly zero, V = e_j)
+    // must stay behind every real column, including real ones whose rounded norm came out <= 0.
+    int I, J;
+    rr_pair(p, round, pair, I, J);
+    const int gcol = tid < JB ? I * JB + tid : J * JB + tid - JB;
+    dsort[tid] = gcol >= nreal ? -1.0 : fmax(H[tid * HLD + tid], 0.0);
+  }
+  __syncthreads();
+  // Newton-Schulz polish  W <- W (1.5 I - 0.5 W'W): the product of ~100 plane rotations per column
+  // drifts from orthogonality by a few 1e-15, which would otherwise accumulate in V over a sweep.
+  for (int idx = tid; idx < JP * JP; idx += 512) {
+    const int i = idx % JP, j = idx / JP;
+    double t = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < JP; ++k) t += W[k * HLD + i] * W[k * HLD + j];
+    H[i * HLD + j] = (i == j ? 1.5 : 0.0) - 0.5 * t;
+  }
+  // de Rijk-style ordering: the rotated columns leave the pair sorted by decreasing norm (the
+  // diagonal of the diagonalised Gram matrix), so large columns migrate to low block indices and
+  // numerically-null ones collect in the last blocks, whose pairs are then skipped outright.
+  // The diagonal was saved to dsort before H is overwritten above.
+  __syncthreads();
+  if (tid < JP) {
+    const double dj = dsort[tid];
+    int rank = 0;
+    for (int i = 0; i < JP; ++i) {
+      const double di = dsort[i];
+      rank += (di > dj || (di == dj && i < tid)) ? 1 : 0;
+    }
+    perm[tid] = rank;
+  }
+  __syncthreads();
   double* wout = Wbuf + (long long)pair * (JP * JP);
   for (int idx = tid; idx < JP * JP; idx += 512) {
     const int k = idx % JP, n = idx / JP;
-    wout[idx] = W[k * HLD + n];
+    double t = 0.0;
+#pragma unroll 8
+    for (int l = 0; l < JP; ++l) t += W[k * HLD + l] * H[l * HLD + n];
+    wout[k + JP * perm[n]] = t;
   }
 }
 
@@ -357,13 +386,25 @@ __global__ void k_load_matrix(double* G, long long ldg, const double* __restrict
 
 __global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
 
-struct Lcg {
-  unsigned long long s;
-  double next() {
-    s = s * 6364136223846793005ULL + 1442695040888963407ULL;
-    return ((double)((s >> 11) & ((1ULL << 53) - 1)) / (double)(1ULL << 53)) - 0.5;
+// E = 1.5 I - 0.5 T in place (Newton-Schulz polish of a warm-start basis)
+__global__ void k_ns_factor(double* T, long long n) {
+  const long long total = n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx % n, j = idx / n;
+    T[idx] = (i == j ? 1.5 : 0.0) - 0.5 * T[idx];
   }
-};
+}
+
+__global__ void k_fill_random(double* p, long long n, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);   // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    p[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+  }
+}
 
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -372,7 +413,7 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
+static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int depth, const Tens* V0) {
   TNAD_REQUIRE(Ain0.rank == 2 || Ain0.rank == 4, "svd: need a matrix or a rank-4 view [(i0,i1),(j0,j1)]");
   Tens Ain = Ain0;
   if (Ain0.rank == 2) {   // promote to rank 4 with unit middle dims
@@ -398,7 +439,7 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
   static bool attr_set = false;
   const size_t smem_gram = (size_t)JP * XLD * sizeof(double);
   const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
-  const size_t smem_eig = (size_t)(2 * JP * HLD + 2 * JB + 16 + JB) * sizeof(double);
+  const size_t smem_eig = (size_t)(2 * JP * HLD + 16 + JP + JP) * sizeof(double);
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eig));
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gram));
@@ -417,6 +458,29 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
     LAUNCH_CHECK(c);
   }
   set_identity(c, Vw.p, ldv, N);
+  if (V0 && !transposed && m == n && V0->rank == 2 && V0->dim[0] == n && V0->dim[1] == n) {
+    // Warm start (CTMRG: successive cpmat are close): V <- polish(V0), G <- A V.  Any orthogonal V
+    // is a valid start for one-sided Jacobi; a good one leaves only a few sweeps of work.
+    Tens Ms = t_alloc(c, {m, n});
+    {
+      Tens Gv = t_wrap(G.p, {m, n});
+      Gv.str[1] = mpad;
+      tcopy(c, Gv, Ms, 1.0, 0.0);
+    }
+    Tens T = contract_new(c, "ki,kj->ij", *V0, *V0);
+    {
+      const long long total = n * n;
+      int nb = (int)std::min<long long>((total + 1023) / 1024, 148 * 8);
+      k_ns_factor<<<nb < 1 ? 1 : nb, 256, 0, c->stream>>>(T.p, n);
+      LAUNCH_CHECK(c);
+    }
+    Tens Vv = t_wrap(Vw.p, {n, n});
+    Vv.str[1] = ldv;
+    contract(c, "ik,kj->ij", *V0, T, Vv, 1.0, 0.0);
+    Tens Gv = t_wrap(G.p, {m, n});
+    Gv.str[1] = mpad;
+    contract(c, "ik,kj->ij", Ms, Vv, Gv, 1.0, 0.0);
+  }
 
   int nsplit = (2 * c->num_sms + npairs - 1) / npairs;
   if (nsplit > mchunks) nsplit = mchunks;
@@ -429,6 +493,11 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
 
   const double eps = 2.220446049250313e-16;
   const double tol = std::max(8.0, 2.0 * std::sqrt((double)m)) * eps;
+  // numerically-null threshold on squared column norms: (4 eps)^2 max(m,n) |A|_F^2
+  const double nullfac = 16.0 * eps * eps * (double)std::max(m, n);
+  double* fro2 = c->scal + 18;
+  reduce(c, RED_SUMSQ, G, nullptr, fro2);
+  const bool debug = env_int("TNAD_JACOBI_DEBUG", 0) != 0;
   const int max_inner = env_int("TNAD_JACOBI_INNER", 4);
   const int max_sweeps = env_int("TNAD_JACOBI_SWEEPS", 60);
 
@@ -442,7 +511,8 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
     for (int r = 0; r < p - 1; ++r) {
       k_jacobi_gram<<<dim3(npairs, nsplit), 256, smem_gram, c->stream>>>(G.p, mpad, mchunks, p, r, nsplit, Hpart.p);
       LAUNCH_CHECK(c);
-      k_jacobi_eig<<<npairs, 512, smem_eig, c->stream>>>(Hpart.p, nsplit, tol, max_inner, Wbuf.p, skip, offbits);
+      k_jacobi_eig<<<npairs, 512, smem_eig, c->stream>>>(Hpart.p, nsplit, tol, max_inner, fro2, nullfac, p, r, (int)n, Wbuf.p, skip,
+                                                        offbits);
       LAUNCH_CHECK(c);
       k_jacobi_update<<<dim3(npairs, mchunks + vchunks), 256, smem_upd, c->stream>>>(G.p, mpad, mchunks, Vw.p, ldv, p,
                                                                                      r, Wbuf.p, skip);
@@ -450,7 +520,8 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
     }
     double off;
     d2h(c, &off, c->scal + 16, 1);
-    if (off <= tol) {
+    if (debug) fprintf(stderr, "[tnad jacobi] m=%lld n=%lld sweep %d off %.3e (tol %.1e)\n", (long long)m, (long long)n, sweep, off, tol);
+    if (off <= 4.0 * tol) {   // rotations are applied down to tol; 4 tol is the rounding floor of the cosines
       converged = true;
       ++sweep;
       break;
@@ -471,6 +542,9 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
   LAUNCH_CHECK(c);
   std::vector<double> s2h((size_t)N);
   d2h(c, s2h.data(), s2.p, (size_t)N);
+  double fro2h;
+  d2h(c, &fro2h, fro2, 1);
+  const double thr2 = nullfac * fro2h;
   std::vector<int> perm((size_t)n);
   std::iota(perm.begin(), perm.end(), 0);
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return s2h[a] > s2h[b]; });
@@ -480,11 +554,8 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
   for (int64_t r = 0; r < n; ++r) {
     const double v = s2h[perm[r]];
     sval[r] = std::sqrt(v);
-    isnull[r] = (v < 1e-280) ? 1 : 0;
-    if (isnull[r]) {
-      sval[r] = std::sqrt(v);
-      nullcols.push_back(r);
-    }
+    isnull[r] = (v <= thr2) ? 1 : 0;
+    if (isnull[r]) nullcols.push_back(r);
   }
   // upload perm / sval / isnull
   Tens meta = t_alloc(c, {3 * n + 4});
@@ -504,27 +575,32 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
   sync(c);   // perm/sval/isnull host vectors must outlive the async uploads
 
   if (!sym && !nullcols.empty()) {
-    // orthonormal completion of the left null space: project random vectors out of span(U), 3 passes
-    Lcg rng{0x9E3779B97F4A7C15ULL};
-    std::vector<double> wh((size_t)m);
-    Tens w = t_alloc(c, {m});
-    Tens cv = t_alloc(c, {n});
-    double* ss = c->scal + 17;
-    for (int64_t r : nullcols) {
-      for (auto& x : wh) x = rng.next();
-      h2d(c, w.p, wh.data(), (size_t)m);
-      for (int pass = 0; pass < 3; ++pass) {
-        contract(c, "mk,m->k", U, w, cv, 1.0, 0.0);
-        contract(c, "mk,k->m", U, cv, w, -1.0, 1.0);
-      }
-      reduce(c, RED_SUMSQ, w, nullptr, ss);
-      Tens col = t_wrap(U.p + r * m, {m});
-      scale_dev(c, w, col, ss, SC_INVSQRT);
-      sync(c);
+    // Orthonormal completion of the left null space (needed because svd_back uses the full U):
+    // project a random block out of span(U_range) twice, then orthonormalise it with the same
+    // Jacobi kernels (left singular vectors of a full-column-rank block).
+    const int64_t q = (int64_t)nullcols.size(), r = n - q;   // nulls sort last
+    TNAD_REQUIRE(depth < 3, "svd: null-space completion did not terminate");
+    Tens Wr = t_alloc(c, {m, q});
+    {
+      const long long total = m * q;
+      int nb = (int)std::min<long long>((total + 1023) / 1024, 148 * 8);
+      k_fill_random<<<nb < 1 ? 1 : nb, 256, 0, c->stream>>>(Wr.p, total, 0x9E3779B97F4A7C15ULL + (unsigned long long)depth);
+      LAUNCH_CHECK(c);
     }
+    if (r > 0) {
+      Tens Ur = t_slice_last(U, 0, r);
+      for (int pass = 0; pass < 2; ++pass) {
+        Tens Cm = contract_new(c, "mr,mq->rq", Ur, Wr);
+        contract(c, "mr,rq->mq", Ur, Cm, Wr, -1.0, 1.0);
+      }
+    }
+    SvdResult wn = svd_jacobi_impl(c, Wr, false, depth + 1, nullptr);
+    TNAD_CUDA(cudaMemcpyAsync(U.p + r * m, wn.U.p, (size_t)(m * q) * sizeof(double), cudaMemcpyDeviceToDevice,
+                              c->stream));
   }
 
   res.s_host = sval;
+  res.null_thr = std::sqrt(thr2);
   if (transposed) {
     res.U = Vo;
     res.V = U;
@@ -534,6 +610,10 @@ SvdResult svd_jacobi(tnad_ctx* c, const Tens& Ain0, bool sym) {
   }
   res.S = S;
   return res;
+}
+
+SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* V0) {
+  return svd_jacobi_impl(c, A, sym_add_transpose, 0, V0);
 }
 
 }  // namespace tnad

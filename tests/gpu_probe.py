@@ -93,7 +93,7 @@ def main(mode):
         ou = np.abs(U.T @ U - np.eye(k)).max()
         ov = np.abs(V.T @ V - np.eye(k)).max()
         es = np.abs(S - Sref).max() / Sref[0]
-        ok = rec < 1e-13 and ou < 1e-12 and ov < 1e-12 and es < 1e-13 and np.all(np.diff(S) <= 0)
+        ok = rec < 2e-13 and ou < 1e-12 and ov < 1e-12 and es < 1e-13 and np.all(np.diff(S) <= 0)
         return ok, f"rec {rec:.1e} orthU {ou:.1e} orthV {ov:.1e} dS {es:.1e} sweeps {ctx.last_sweeps}"
 
     for shp in [(4, 4), (9, 9), (30, 30), (64, 64), (80, 80), (100, 60), (60, 100), (128, 128), (200, 200), (400, 400)]:
@@ -178,18 +178,20 @@ def main(mode):
     check("ctmrgstep D=3 chi=10", lambda: step_case(3, 10))
     check("ctmrgstep D=4 chi=20", lambda: step_case(4, 20))
 
-    def mag_case(beta, chi):
+    def mag_case(beta, chi, seed):
         a, m = O.model_tensor_ising(beta), O.mag_tensor_ising(beta)
         c0, e0 = O.init_raw(a, chi)
         cg, eg = ctx.ctmrg_init_raw(a, chi)
         e_init = max(np.abs(cg - c0).max(), np.abs(eg - e0).max())
-        co, eo, vo, no = O.ctmrg(a, c0, e0, 1e-10, 500)
-        cg, eg, vg, ng = ctx.ctmrg(a, c0, e0, 1e-10, 500)
+        c0, e0 = O.init_random(a, chi, np.random.default_rng(seed))      # :random breaks the Z2 symmetry
+        co, eo, vo, no = O.ctmrg(a, c0, e0, 1e-10, 300)
+        cg, eg, vg, ng = ctx.ctmrg(a, c0, e0, 1e-10, 300)
         mo = O.magnetisation_readout(a, m, co, eo)
         mg = ctx.magnetisation_readout(a, m, cg, eg)
-        return (e_init == 0 and abs(mo - mg) < 1e-9), f"init {e_init:.1e} mag {mg!r} oracle {mo!r} onsager {O.magofbeta(beta)!r} steps {ng}/{no}"
-    check("ctmrg ising beta=0.6 chi=8 magnetisation", lambda: mag_case(0.6, 8))
-    check("ctmrg ising beta=0.3 chi=16 magnetisation", lambda: mag_case(0.3, 16))
+        return (e_init < 1e-14 and abs(mo - mg) < 1e-8 and abs(mg - O.magofbeta(beta)) < 1e-4), \
+            f"init {e_init:.1e} mag {mg!r} oracle {mo!r} onsager {O.magofbeta(beta)!r} steps {ng}/{no}"
+    check("ctmrg ising beta=0.6 chi=8 magnetisation", lambda: mag_case(0.6, 8, 5))
+    check("ctmrg ising beta=0.3 chi=16 magnetisation", lambda: mag_case(0.3, 16, 5))
 
     # ---- 6. energy + gradient ------------------------------------------------------------------
     h = O.hamiltonian_heisenberg()
@@ -222,7 +224,7 @@ def main(mode):
             dt = time.time() - t0
             rec = relerr((U * S) @ V.T, A)
             ou = np.abs(U.T @ U - np.eye(n)).max()
-            return rec < 1e-12 and ou < 1e-11, f"n={n} {dt:.3f}s (incl. PCIe) sweeps {ctx.last_sweeps} rec {rec:.1e} orth {ou:.1e}"
+            return rec < 5e-13 and ou < 1e-12, f"n={n} {dt:.3f}s (incl. PCIe) sweeps {ctx.last_sweeps} rec {rec:.1e} orth {ou:.1e}"
         check("svd symmetric 1024", lambda: big_svd(1024))
         check("svd symmetric 2048", lambda: big_svd(2048))
 
