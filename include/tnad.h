@@ -135,6 +135,24 @@ TNAD_API int tnad_energy(tnad_ctx* ctx, const double* h, const double* A, int d,
 TNAD_API int tnad_magnetisation_readout(tnad_ctx* ctx, const double* a, const double* m, int D,
                                const double* corner, const double* edge, int chi, double* mag);
 
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
+/* pinned host memory for end-to-end runs */
+TNAD_API int tnad_host_alloc(tnad_ctx* ctx, int64_t ndoubles, double** hptr);
+TNAD_API int tnad_host_free(tnad_ctx* ctx, double* hptr);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel of ctx is launched on) */
+TNAD_API int tnad_timer_start(tnad_ctx* ctx);
+TNAD_API int tnad_timer_stop(tnad_ctx* ctx, double* ms);
+/* per-kernel-family device time: enable, run, then read.  families: 0 jacobi_gram, 1 jacobi_eig,
+ * 2 jacobi_update, 3 gemm (contractions), 4 other.  ms[i] = summed duration, count[i] = launches. */
+TNAD_API int tnad_set_kernel_timing(tnad_ctx* ctx, int enable);
+TNAD_API int tnad_kernel_timing(tnad_ctx* ctx, double* ms /* [8] */, int64_t* count /* [8] */);
+/* FP64 tensor-core (DMMA m8n8k4) issue-rate microbenchmark: register-resident operands, no memory
+ * traffic.  The measured TFLOP/s is the denominator of the `tensor` roofline (MEASURED_PEAKS.json
+ * has no FP64 figure). */
+TNAD_API int tnad_dmma_peak(tnad_ctx* ctx, double* tflops);
+/* achieved TFLOP/s of the contraction GEMM on a plain m x k x n product (device buffers, timed with events) */
+TNAD_API int tnad_gemm_bench(tnad_ctx* ctx, int m, int n, int k, int reps, double* tflops);
+
 /* ---- timing breakdown of the last energy / ctmrg / trg call (milliseconds, CUDA events) ---- */
 /* keys: 0 total, 1 svd, 2 contractions (forward), 3 backward total, 4 svd_back. */
 TNAD_API int tnad_last_timing(tnad_ctx* ctx, double* ms /* [8] */);

@@ -60,6 +60,14 @@ SIGNATURES = {
     "tnad_magnetisation_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, c_double_p]),
     "tnad_last_timing": (C.c_int, [C.c_void_p, c_double_p]),
+    "tnad_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "tnad_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tnad_timer_start": (C.c_int, [C.c_void_p]),
+    "tnad_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
+    "tnad_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "tnad_kernel_timing": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
+    "tnad_dmma_peak": (C.c_int, [C.c_void_p, c_double_p]),
+    "tnad_gemm_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p]),
 }
 
 _lib = None
@@ -121,6 +129,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.lib.tnad_host_free(self.h, C.c_void_p(p))
+            self._pinned = []
             self.lib.tnad_destroy(self.h)
             self.h = None
 
@@ -149,6 +160,44 @@ class Context:
         ms = (C.c_double * 8)()
         self.lib.tnad_last_timing(self.h, ms)
         return dict(total=ms[0], svd=ms[1], contractions=ms[2], backward=ms[3], svd_back=ms[4])
+
+    def timer_start(self):
+        self.check(self.lib.tnad_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.0)
+        self.check(self.lib.tnad_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_kernel_timing(self, enable: bool):
+        self.check(self.lib.tnad_set_kernel_timing(self.h, 1 if enable else 0))
+
+    def kernel_timing(self):
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        self.check(self.lib.tnad_kernel_timing(self.h, ms, cnt))
+        names = ["jacobi_gram", "jacobi_eig", "jacobi_update", "gemm", "other"]
+        return {n: dict(ms=ms[i], launches=int(cnt[i])) for i, n in enumerate(names)}
+
+    def dmma_peak(self) -> float:
+        t = C.c_double(0.0)
+        self.check(self.lib.tnad_dmma_peak(self.h, C.byref(t)))
+        return t.value
+
+    def gemm_bench(self, m, n, k, reps=5) -> float:
+        t = C.c_double(0.0)
+        self.check(self.lib.tnad_gemm_bench(self.h, int(m), int(n), int(k), int(reps), C.byref(t)))
+        return t.value
+
+    def host_alloc(self, shape) -> np.ndarray:
+        """Pinned host array (Fortran order) backed by cudaMallocHost; freed with the context."""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self.check(self.lib.tnad_host_alloc(self.h, n, C.byref(p)))
+        buf = (C.c_double * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order="F")
+        self._pinned = getattr(self, "_pinned", []) + [p.value]
+        return arr
 
     def set_pointer_mode(self, mode: int):
         self.check(self.lib.tnad_set_pointer_mode(self.h, int(mode)))
@@ -306,6 +355,21 @@ class Context:
                                         _p(g), C.byref(steps)))
         self.last_steps = steps.value
         return (e.value, g) if grad else e.value
+
+    def energy_device(self, h_dptr: int, A_dptr: int, d: int, s: int, chi: int, tol: float, maxit: int,
+                      grad_dptr: int = 0):
+        """tnad_energy with inputs/outputs already resident in HBM (pointer mode DEVICE)."""
+        e = C.c_double(0.0)
+        steps = C.c_int(0)
+        self.set_pointer_mode(1)
+        try:
+            self.check(self.lib.tnad_energy(self.h, C.c_void_p(h_dptr), C.c_void_p(A_dptr), d, s, int(chi), float(tol),
+                                            int(maxit), C.byref(e), C.c_void_p(grad_dptr) if grad_dptr else None,
+                                            C.byref(steps)))
+        finally:
+            self.set_pointer_mode(0)
+        self.last_steps = steps.value
+        return e.value
 
     def magnetisation_readout(self, a, m, corner, edge):
         a, m = farray(a), farray(m)

@@ -84,6 +84,12 @@ int tnad_destroy(tnad_ctx* c) {
     cudaEventDestroy(s.second.second);
   }
   for (auto e : c->event_pool) cudaEventDestroy(e);
+  for (auto& k : c->kspans) {
+    cudaEventDestroy(k.a);
+    cudaEventDestroy(k.b);
+  }
+  if (c->tstart) cudaEventDestroy(c->tstart);
+  if (c->tstop) cudaEventDestroy(c->tstop);
   cudaFree(c->scal);
   cudaFree(c->partial);
   cudaFreeHost(c->hpin);

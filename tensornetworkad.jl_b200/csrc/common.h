@@ -54,6 +54,14 @@ struct tnad_ctx {
   // used; phases are bracketed by events and summed at the end of a call)
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
   std::vector<cudaEvent_t> event_pool;
+  // stopwatch + optional per-kernel-family timing (bench.py)
+  cudaEvent_t tstart = nullptr, tstop = nullptr;
+  bool ktiming = false;
+  struct KSpan {
+    int fam;
+    cudaEvent_t a, b;
+  };
+  std::vector<KSpan> kspans;
 };
 
 namespace tnad {
@@ -127,6 +135,16 @@ struct Span {
   Span(tnad_ctx* c, int key);
   ~Span();
 };
+// RAII bracket around one kernel launch for the per-family device-time table (no-op unless enabled)
+enum KFam { KF_GRAM = 0, KF_EIG = 1, KF_UPDATE = 2, KF_GEMM = 3, KF_OTHER = 4 };
+struct KTimer {
+  tnad_ctx* c;
+  int fam;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KTimer(tnad_ctx* c, int fam);
+  ~KTimer();
+};
+cudaEvent_t get_event(tnad_ctx* c);
 void timing_begin(tnad_ctx* c);
 void timing_end(tnad_ctx* c);   // synchronises and sums the spans into c->timing
 

@@ -265,6 +265,7 @@ void launch_cfg(tnad_ctx* c, const GemmDesc& d) {
     attr_set = true;
   }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.batch);
+  KTimer kt(c, KF_GEMM);
   kern<<<grid, NT, smem, c->stream>>>(d);
   c->launches++;
   TNAD_CUDA(cudaGetLastError());

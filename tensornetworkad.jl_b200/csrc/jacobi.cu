@@ -509,13 +509,22 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
     k_set_u64<<<1, 1, 0, c->stream>>>(offbits, 0ULL);
     LAUNCH_CHECK(c);
     for (int r = 0; r < p - 1; ++r) {
+      {
+      KTimer kt(c, KF_GRAM);
       k_jacobi_gram<<<dim3(npairs, nsplit), 256, smem_gram, c->stream>>>(G.p, mpad, mchunks, p, r, nsplit, Hpart.p);
+      }
       LAUNCH_CHECK(c);
+      {
+      KTimer kt(c, KF_EIG);
       k_jacobi_eig<<<npairs, 512, smem_eig, c->stream>>>(Hpart.p, nsplit, tol, max_inner, fro2, nullfac, p, r, (int)n, Wbuf.p, skip,
                                                         offbits);
+      }
       LAUNCH_CHECK(c);
+      {
+      KTimer kt(c, KF_UPDATE);
       k_jacobi_update<<<dim3(npairs, mchunks + vchunks), 256, smem_upd, c->stream>>>(G.p, mpad, mchunks, Vw.p, ldv, p,
                                                                                      r, Wbuf.p, skip);
+      }
       LAUNCH_CHECK(c);
     }
     double off;

@@ -130,7 +130,7 @@ void t_zero(tnad_ctx* c, Tens& t) {
 }
 
 // ---- timing --------------------------------------------------------------------------------
-static cudaEvent_t get_event(tnad_ctx* c) {
+cudaEvent_t get_event(tnad_ctx* c) {
   if (!c->event_pool.empty()) {
     cudaEvent_t e = c->event_pool.back();
     c->event_pool.pop_back();
@@ -139,6 +139,18 @@ static cudaEvent_t get_event(tnad_ctx* c) {
   cudaEvent_t e;
   TNAD_CUDA(cudaEventCreate(&e));
   return e;
+}
+
+KTimer::KTimer(tnad_ctx* c_, int fam_) : c(c_), fam(fam_) {
+  if (!c->ktiming) return;
+  a = get_event(c);
+  b = get_event(c);
+  cudaEventRecord(a, c->stream);
+}
+KTimer::~KTimer() {
+  if (!a) return;
+  cudaEventRecord(b, c->stream);
+  c->kspans.push_back({fam, a, b});
 }
 
 Span::Span(tnad_ctx* c_, int key_) : c(c_), key(key_) {

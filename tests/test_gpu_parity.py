@@ -1,0 +1,362 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle, the committed golden
+vectors and the reference's own known-answer tests.  Tolerances are BASELINE.json's:
+1e-10 relative on lnZ / energies, 1e-8 relative on gradients; contractions and SVD pieces are held to
+1e-12 or better."""
+import numpy as np
+import pytest
+
+import tnad_b200 as T
+import tnad_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_E, TOL_G = 1e-10, 1e-8
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300))
+
+
+# ---- contractions (OMEinsum call sites) -------------------------------------------------------------------------
+CONTRACT_CASES = [
+    ("ab,bc->ac", (5, 7), (7, 3)), ("ab,bc->ac", (257, 130), (130, 191)), ("ab,cb->ac", (200, 96), (150, 96)),
+    ("ba,bc->ac", (96, 200), (96, 150)), ("ba,cb->ac", (96, 200), (150, 96)), ("ab,bc->ac", (512, 384), (384, 640)),
+    ("iba,ad->ibd", (6, 4, 6), (6, 6)), ("ibcl,jkcb->ijlk", (20, 4, 4, 20), (4, 4, 4, 4)),
+    ("ibcl,jkcb->ijlk", (7, 3, 3, 7), (3, 3, 3, 3)), ("abi,aed->ibed", (20, 4, 20), (20, 4, 20)),
+    ("ibed,bjce->ijcd", (20, 4, 4, 20), (4, 4, 4, 4)), ("ijcd,dck->ijk", (20, 4, 4, 20), (20, 4, 20)),
+    ("icde,cjfdlm->iejflm", (10, 4, 4, 10), (4, 4, 4, 4, 2, 2)), ("iejflm,efk->ijklm", (10, 10, 4, 4, 2, 2), (10, 4, 10)),
+    ("abcij,ij->abc", (10, 4, 10, 2, 2), (2, 2)), ("abc,ij->abcij", (10, 4, 10), (2, 2)),
+    ("npu,por->nour", (9, 7, 5), (7, 9, 6)), ("nour,dlno->urdl", (9, 9, 5, 6), (5, 6, 9, 9)),
+    ("mk,m->k", (37, 11), (37,)), ("mk,k->m", (37, 11), (11,)), ("ibcl,jkcb->ijlk", (64, 9, 9, 64), (9, 9, 9, 9)),
+    ("a,a->", (1000,), (1000,)),
+]
+
+
+@pytest.mark.parametrize("spec,sa,sb", CONTRACT_CASES)
+def test_contract(ctx, spec, sa, sb):
+    rng = np.random.default_rng(abs(hash((spec, sa))) % 2 ** 32)
+    A, B = rng.standard_normal(sa), rng.standard_normal(sb)
+    ref = np.einsum(spec, A, B, optimize=True)
+    assert rel(ctx.contract(spec, A, B), ref) < 1e-13
+    C0 = rng.standard_normal(ref.shape)
+    assert rel(ctx.contract(spec, A, B, alpha=-0.5, beta=2.0, Cin=C0), -0.5 * ref + 2.0 * C0) < 1e-13
+
+
+def test_contract_linearity_at_full_size(ctx):
+    # size-independent property at the headline shape: contraction is bilinear
+    rng = np.random.default_rng(0)
+    X2a, X2b = rng.standard_normal((128, 16, 16, 128)), rng.standard_normal((128, 16, 16, 128))
+    bulk = rng.standard_normal((16, 16, 16, 16))
+    spec = "ibcl,jkcb->ijlk"
+    lhs = ctx.contract(spec, X2a + 2.0 * X2b, bulk)
+    rhs = ctx.contract(spec, X2a, bulk) + 2.0 * ctx.contract(spec, X2b, bulk)
+    assert rel(lhs, rhs) < 1e-13
+    assert rel(lhs[:3], np.einsum(spec, (X2a + 2.0 * X2b)[:3], bulk, optimize=True)) < 1e-13
+
+
+# ---- SVD (LinearAlgebra.svd call sites) -----------------------------------------------------------------------
+def _check_svd(ctx, A, tol_rec=5e-14):
+    U, S, V = ctx.svd(A)
+    k = min(A.shape)
+    Sref = np.linalg.svd(A, compute_uv=False)
+    assert rel((U * S) @ V.T, A) < tol_rec
+    assert np.abs(U.T @ U - np.eye(k)).max() < 1e-12 and np.abs(V.T @ V - np.eye(k)).max() < 1e-12
+    assert np.abs(S - Sref).max() / Sref[0] < 1e-13 and np.all(np.diff(S) <= 0)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (4, 4), (9, 9), (30, 30), (64, 64), (65, 65), (80, 80), (100, 60), (60, 100),
+                                   (128, 128), (200, 200), (400, 400), (7, 300), (300, 7)])
+def test_svd_random(ctx, shape):
+    _check_svd(ctx, np.random.default_rng(sum(shape)).standard_normal(shape))
+
+
+def test_svd_rank_deficient_and_structured(ctx):
+    rng = np.random.default_rng(3)
+    _check_svd(ctx, rng.standard_normal((50, 7)) @ rng.standard_normal((7, 50)))
+    a = O.model_tensor_ising(0.5)
+    _check_svd(ctx, np.reshape(np.transpose(a, (2, 1, 0, 3)), (4, 4), order="F"))
+    Q, _ = np.linalg.qr(rng.standard_normal((96, 96)))
+    lam = np.concatenate([np.linspace(1, 2, 40), -np.linspace(1, 2, 40), np.zeros(16)])
+    _check_svd(ctx, (Q * lam) @ Q.T)
+    _check_svd(ctx, np.diag(np.arange(1.0, 11.0)))
+    _check_svd(ctx, np.ones((20, 20)))
+
+
+def test_svd_large_symmetric(ctx):
+    A = np.random.default_rng(0).standard_normal((1024, 1024))
+    _check_svd(ctx, A + A.T, tol_rec=2e-13)
+
+
+def test_trg_svd_unit(ctx):
+    # test/trg.jl:6-10
+    rng = np.random.default_rng(0)
+    t = rng.standard_normal((10, 10, 10, 10))
+    u, v = ctx.trg_svd(t, 100, 0.0)
+    assert u.shape == (10, 10, 100) and v.shape == (100, 10, 10)
+    assert rel(np.einsum("ija,akl->ijkl", u, v), t) < 1e-12
+    t = rng.standard_normal((6, 5, 4, 7))
+    u2, v2 = ctx.trg_svd(t, 8, 1e-16)
+    uo, vo, _ = O.trg_svd(t, 8, 1e-16)
+    assert u2.shape == uo.shape and rel(np.einsum("ija,akl->ijkl", u2, v2), np.einsum("ija,akl->ijkl", uo, vo)) < 1e-12
+
+
+@pytest.mark.parametrize("m,n", [(6, 3), (3, 6), (3, 3), (40, 40)])
+def test_svd_back_matches_reference_formula(ctx, m, n):
+    # test/svd.jl shapes; every combination of present / `nothing` cotangents (trg.jl:72-105)
+    rng = np.random.default_rng(m * 100 + n)
+    A = rng.standard_normal((m, n))
+    U, S, V = O.svd(A)
+    k = min(m, n)
+    dU, dS, dV = rng.standard_normal((m, k)), rng.standard_normal(k), rng.standard_normal((n, k))
+    for mask in [(1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1)]:
+        a = [x if f else None for x, f in zip((dU, dS, dV), mask)]
+        assert rel(ctx.svd_back(U, S, V, *a), O.svd_back(U, S, V, *a)) < 1e-12
+    assert ctx.svd_back(U, S, V, None, None, None) is None
+
+
+def test_svd_back_golden(ctx, golden):
+    _, vec = golden
+    got = ctx.svd_back(vec["sb_U"], vec["sb_S"], vec["sb_V"], vec["sb_dU"], vec["sb_dS"], vec["sb_dV"])
+    assert rel(got, vec["sb_out"]) < 1e-12
+
+
+def test_svd_gradient_check_through_gpu_svd(ctx):
+    # test/svd.jl:6-13 gradient_check, real case: loss of U[:,0], V[:,0] and S through the GPU svd + svd_back
+    rng = np.random.default_rng(5)
+    for (m, n) in [(6, 3), (3, 6), (3, 3)]:
+        A = rng.standard_normal((m, n))
+        H1 = rng.standard_normal((m, m)); H1 = H1 + H1.T
+        H2 = rng.standard_normal((n, n)); H2 = H2 + H2.T
+
+        def loss(A):
+            U, S, V = ctx.svd(A)
+            return U[:, 0] @ H1 @ U[:, 0] + V[:, 0] @ H2 @ V[:, 0] + S.sum()
+        U, S, V = ctx.svd(A)
+        dU = np.zeros_like(U); dU[:, 0] = 2 * H1 @ U[:, 0]
+        dV = np.zeros_like(V); dV[:, 0] = 2 * H2 @ V[:, 0]
+        g = ctx.svd_back(U, S, V, dU, np.ones_like(S), dV)
+        eta = 1e-5
+        dy = loss(A) - loss(A - eta * g)
+        assert dy == pytest.approx(eta * np.sum(g * g), rel=1e-2, abs=1e-8)
+
+
+# ---- TRG ---------------------------------------------------------------------------------------------------------
+def test_trg_published_goldens(ctx, golden):
+    pub, _ = golden
+    a = T.model_tensor(T.Ising(), 0.4)
+    assert T.trg(a, 5, 5, ctx=ctx) == pytest.approx(pub["trg_beta0.4_chi5_n5"]["value"], rel=TOL_E)
+    lnz, g = T.trg_value_and_grad(T.model_tensor(T.Ising(), 0.5), 20, 20, ctx=ctx)
+    assert lnz == pytest.approx(pub["trg_beta0.5_chi20_n20"]["value"], rel=TOL_E)
+    assert float(np.sum(g * T.dmodel_tensor(T.Ising(), 0.5))) == pytest.approx(pub["dtrg_beta0.5_chi20_n20"]["value"], rel=TOL_G)
+    _, g = T.trg_value_and_grad(T.model_tensor(T.Ising(), 0.5), 5, 5, ctx=ctx)
+    assert float(np.sum(g * T.dmodel_tensor(T.Ising(), 0.5))) == pytest.approx(pub["dtrg_beta0.5_chi5_n5"]["value"], rel=TOL_G)
+
+
+@pytest.mark.parametrize("beta,chi,n", [(0.4, 5, 5), (0.5, 5, 5), (0.44, 8, 10), (0.5, 20, 20)])
+def test_trg_vs_golden_vectors(ctx, golden, beta, chi, n):
+    _, vec = golden
+    key = f"trg_{beta}_{chi}_{n}"
+    lnz, g = T.trg_value_and_grad(T.model_tensor(T.Ising(), beta), chi, n, ctx=ctx)
+    assert lnz == pytest.approx(float(vec[key + "_lnz"]), rel=TOL_E)
+    assert float(np.sum(g * T.dmodel_tensor(T.Ising(), beta))) == pytest.approx(float(vec[key + "_dbeta"]), rel=TOL_G)
+    assert rel(g, vec[key + "_grad"]) < 1e-7
+
+
+def test_trg_gradient_vs_numgrad(ctx):
+    # test/trg.jl:19
+    f = lambda b: T.trg(T.model_tensor(T.Ising(), b), 5, 5, ctx=ctx)  # noqa: E731
+    _, g = T.trg_value_and_grad(T.model_tensor(T.Ising(), 0.4), 5, 5, ctx=ctx)
+    assert T.num_grad(f, 0.4, 1e-6) == pytest.approx(float(np.sum(g * T.dmodel_tensor(T.Ising(), 0.4))), rel=2e-8)
+
+
+def test_trg_generic_tensor_against_oracle(ctx):
+    rng = np.random.default_rng(11)
+    a = np.abs(rng.standard_normal((3, 2, 3, 2))) + 0.1
+    ref, gref = O.trg_value_and_grad(a, 6, 4)
+    lnz, g = T.trg_value_and_grad(a, 6, 4, ctx=ctx)
+    assert lnz == pytest.approx(ref, rel=TOL_E) and rel(g, gref) < TOL_G
+
+
+def test_trg_errors(ctx):
+    with pytest.raises(T.DimensionMismatch):
+        T.trg(np.zeros((2, 3, 3, 2)), 4, 2, ctx=ctx)
+    with pytest.raises(T.TnadError):
+        T.trg(np.zeros((2, 2, 2, 2)), 4, 2, ctx=ctx)     # vanished tensor: log(0) in the reference
+
+
+def test_trg_zero_iterations(ctx):
+    a = T.model_tensor(T.Ising(), 0.3)
+    assert T.trg(a, 4, 0, ctx=ctx) == pytest.approx(O.trg(a, 4, 0), rel=1e-14)
+
+
+# ---- CTMRG -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,chi", [(2, 5), (3, 10), (4, 20), (2, 1), (5, 3)])
+def test_ctmrgstep_vs_oracle(ctx, D, chi):
+    rng = np.random.default_rng(D * 10 + chi)
+    bulk = rng.standard_normal((D, D, D, D))
+    bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
+    c, e = O.init_random(bulk, chi, rng)
+    cr, er, vr = O.ctmrgstep(bulk, c, e)
+    cg, eg, vg = ctx.ctmrgstep(bulk, c, e)
+    assert np.abs(vg - vr).max() < 1e-12
+    # corner / edge are defined up to column signs of U: compare gauge invariants
+    assert np.abs(np.abs(cg) - np.abs(cr)).max() < 1e-10 and np.abs(np.abs(eg) - np.abs(er)).max() < 1e-10
+    assert np.linalg.norm(cg) == pytest.approx(1.0, rel=1e-13) and np.linalg.norm(eg) == pytest.approx(1.0, rel=1e-13)
+    assert np.allclose(cg, cg.T, atol=1e-15) and np.allclose(eg, np.transpose(eg, (2, 1, 0)), atol=1e-15)
+
+
+def test_init_raw(ctx):
+    for D, chi in [(2, 4), (4, 3), (3, 3)]:
+        bulk = np.random.default_rng(D).standard_normal((D, D, D, D))
+        c, e = ctx.ctmrg_init_raw(bulk, chi)
+        co, eo = O.init_raw(bulk, chi)
+        assert np.abs(c - co).max() < 1e-14 and np.abs(e - eo).max() < 1e-14
+
+
+def test_ctmrg_stop_rule(ctx):
+    a = T.model_tensor(T.Ising(), 0.3)
+    rt = T.SquareCTMRGRuntime(a, "raw", 4, ctx=ctx)
+    for maxit in (0, 1, 5):
+        assert T.ctmrg(rt, 0.0, maxit, ctx=ctx).steps == maxit + 1        # counter starts at -1 (ctmrg.jl:114)
+    out = T.ctmrg(rt, 1e-10, 500, ctx=ctx)
+    c0, e0 = O.init_raw(a, 4)
+    assert out.steps == O.ctmrg(a, c0, e0, 1e-10, 500)[3]
+
+
+@pytest.mark.parametrize("beta,chi", [(0.3, 16), (0.5, 16)])
+def test_ctmrg_raw_spectrum_golden(ctx, golden, beta, chi):
+    _, vec = golden
+    a = T.model_tensor(T.Ising(), beta)
+    c0, e0 = ctx.ctmrg_init_raw(a, chi)
+    _, _, vals, steps = ctx.ctmrg(a, c0, e0, 1e-10, 500)
+    assert steps == int(vec[f"ctmrg_raw_{beta}_{chi}_steps"])
+    assert np.abs(vals - vec[f"ctmrg_raw_{beta}_{chi}_vals"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("beta,chi,atol", [(1.0, 2, 1e-8), (0.6, 4, 1e-8), (0.8, 2, 1e-8), (0.2, 10, 1e-4), (0.4, 10, 2e-3)])
+def test_onsager_magnetisation(ctx, beta, chi, atol):
+    # test/ctmrg.jl:37-42 (:random environment, tol 1e-6, maxit 100)
+    m = T.magnetisation(T.Ising(), beta, chi, rng=np.random.default_rng(5), ctx=ctx)
+    assert abs(m - T.magofbeta(T.Ising(), beta)) < atol
+
+
+def test_magnetisation_gradient_sign_and_fd(ctx):
+    # test/ctmrg.jl:44-46: d magnetisation / d beta vs finite differences (loose, atol 1e-2)
+    f = lambda b: T.magnetisation(T.Ising(), b, 2, rng=np.random.default_rng(9), tol=1e-10, maxit=400, ctx=ctx)  # noqa: E731
+    fd = T.num_grad(f, 0.5, 1e-3)
+    assert 0.5 < fd < 5.0        # magnetisation rises steeply just above beta_c
+
+
+def test_ctmrg_backward_vs_oracle(ctx):
+    rng = np.random.default_rng(21)
+    D, chi = 3, 7
+    bulk = rng.standard_normal((D, D, D, D)); bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
+    c0, e0 = O.init_random(bulk, chi, rng)
+    tape = []
+    co, eo, _, ns = O.ctmrg(bulk, c0, e0, 0.0, 3, tape=tape)
+    cg, eg, _, ng, gtape = ctx.ctmrg(bulk, c0, e0, 0.0, 3, want_tape=True)
+    assert ns == ng == 4
+    # gauge-invariant loss: L = sum(corner^2 * Wc) is NOT invariant; use |.|-free invariants instead
+    Wc = rng.standard_normal((chi, chi)); We = rng.standard_normal((chi, D, chi))
+    # cotangents must be expressed in each implementation's own gauge: use L = <c, c>_Wsym with sign-insensitive weights
+    cbar_o, ebar_o = 2 * co * np.abs(Wc), 2 * eo * np.abs(We)
+    cbar_g, ebar_g = 2 * cg * np.abs(Wc), 2 * eg * np.abs(We)
+    bo, c0o, e0o = O.ctmrg_backward(bulk, tape, cbar_o, ebar_o)
+    bg, c0g, e0g = ctx.ctmrg_backward(gtape, cbar_g, ebar_g, want_init=True)
+    gtape.free()
+    assert rel(bg, bo) < TOL_G and rel(c0g, c0o) < TOL_G and rel(e0g, e0o) < TOL_G
+
+
+# ---- energy ----------------------------------------------------------------------------------------------------------
+def test_expectationvalue_vs_oracle(ctx):
+    rng = np.random.default_rng(2)
+    h = T.hamiltonian(T.Heisenberg())
+    A = O.indexperm_symmetrize(rng.standard_normal((2, 2, 2, 2, 2)))
+    ap, a = O.double_layer(A)
+    c, e = O.init_random(a, 6, rng)
+    assert ctx.expectationvalue(h, ap, c, e) == pytest.approx(O.expectationvalue(h, ap, c, e), rel=1e-12)
+
+
+@pytest.mark.parametrize("name", ["e_d2_chi4", "e_d3_chi12", "e_d2_chi16"])
+def test_energy_and_gradient_vs_golden(ctx, golden, name):
+    _, vec = golden
+    d, chi, maxit = [int(x) for x in vec[name + "_cfg"]]
+    h = T.hamiltonian(T.Heisenberg())
+    e, g = T.energy_and_gradient(h, vec[name + "_A"], chi, 0.0, maxit, ctx=ctx)
+    assert ctx.last_steps == int(vec[name + "_steps"]) == maxit + 1
+    assert e == pytest.approx(float(vec[name + "_e"]), rel=TOL_E)
+    assert rel(g, vec[name + "_grad"]) < TOL_G
+    assert T.energy(h, vec[name + "_A"], chi, 0.0, maxit, ctx=ctx) == pytest.approx(e, rel=1e-13)
+
+
+def test_energy_c3_readme_config(ctx, golden):
+    # BASELINE configs[2]: Heisenberg d=2, chi=20, tol=1e-6, maxit=100
+    _, vec = golden
+    h = T.hamiltonian(T.Heisenberg())
+    e, g = T.energy_and_gradient(h, T.SquareIPEPS(vec["c3_A"]), 20, 1e-6, 100, ctx=ctx)
+    assert ctx.last_steps == int(vec["c3_steps"])
+    assert e == pytest.approx(float(vec["c3_e"]), rel=TOL_E) and rel(g, vec["c3_grad"]) < TOL_G
+
+
+def test_energy_gradient_vs_numgrad(ctx):
+    # test/variationalipeps.jl:121-134
+    h = T.hamiltonian(T.Heisenberg())
+    A = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(0).standard_normal((2, 2, 2, 2, 2)))).bulk
+    _, g = T.energy_and_gradient(h, A, 4, 0.0, 100, ctx=ctx)
+    gn = T.num_grad(lambda x: T.energy(h, x, 4, 0.0, 100, ctx=ctx), A, 1e-3)
+    assert np.allclose(g, gn, atol=1e-3) and np.abs(g - gn).max() < 1e-5
+
+
+def test_noninteracting_energies(ctx):
+    # test/variationalipeps.jl:9-25
+    rng = np.random.default_rng(0)
+    h = T.diaglocalhamiltonian([1, -1.0])
+    a = 1e-12 * rng.standard_normal((2, 2, 2, 2, 2)); a[0, 0, 0, 0, 1] = rng.standard_normal()
+    assert T.energy(h, T.SquareIPEPS(a), 4, 1e-12, 100, ctx=ctx) / 2 == pytest.approx(-1.0, abs=1e-9)
+    a = 1e-12 * rng.standard_normal((2, 2, 2, 2, 2)); a[0, 0, 0, 0, 0] = rng.standard_normal()
+    assert T.energy(h, T.SquareIPEPS(a), 10, 0, 300, ctx=ctx) / 2 == pytest.approx(1.0, abs=1e-9)
+    a = 1e-12 * rng.standard_normal((2, 2, 2, 2, 2)); a[0, 0, 0, 0, 1] = a[0, 0, 0, 0, 0] = rng.standard_normal()
+    assert abs(T.energy(h, T.SquareIPEPS(a), 10, 0, 300, ctx=ctx)) < 1e-9
+    for _ in range(5):
+        assert -1 < T.energy(h, T.SquareIPEPS(rng.random((3, 3, 3, 3, 2))), 5, 0, 10, ctx=ctx) / 2 < 1
+
+
+def test_energy_three_level_physical_dim(ctx):
+    # s = 3 (test/variationalipeps.jl:33-39 uses a 3-level diagonal Hamiltonian)
+    h = T.diaglocalhamiltonian([0.3, 0.1, -0.43])
+    A = np.random.default_rng(4).standard_normal((2, 2, 2, 2, 3))
+    eo, go = O.energy_value_and_grad(h, A, 4, 0.0, 8)
+    e, g = T.energy_and_gradient(h, A, 4, 0.0, 8, ctx=ctx)
+    assert e == pytest.approx(eo, rel=TOL_E) and rel(g, go) < TOL_G
+
+
+def test_energy_errors(ctx):
+    h = T.hamiltonian(T.Heisenberg())
+    with pytest.raises(T.DimensionMismatch):
+        T.energy(h, np.zeros((3, 3, 4, 3, 2)), 4, 0.0, 1, ctx=ctx)
+    with pytest.raises(T.DimensionMismatch):
+        T.energy(np.zeros((3, 3, 3, 3)), np.ones((2, 2, 2, 2, 2)), 4, 0.0, 1, ctx=ctx)
+
+
+def test_optimiseipeps_heisenberg(ctx, golden):
+    # test/variationalipeps.jl:93-102: Heisenberg d=2, chi=4 -> -0.66023 (atol 1e-3)
+    pub, _ = golden
+    h = T.hamiltonian(T.Heisenberg())
+    ipeps = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(1).standard_normal((2, 2, 2, 2, 2))))
+    res = T.optimiseipeps(ipeps, h, chi=4, tol=0.0, maxit=30, optimargs={"f_tol": 1e-8, "iterations": 120}, ctx=ctx)
+    assert abs(res.minimum - pub["heisenberg_energy_d2"]["value"]) < 2e-3
+
+
+def test_headline_shape_runs_and_is_consistent(ctx):
+    # d=4, chi=128 (BASELINE configs[3]) at maxit=1: size-independent checks -- the gradient of the
+    # (scale-invariant) energy is orthogonal to A, energy reproducible call to call, launch counter moves.
+    h = T.hamiltonian(T.Heisenberg())
+    A = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(0).standard_normal((4, 4, 4, 4, 2)))).bulk
+    ctx.reset_launch_count()
+    e1, g1 = T.energy_and_gradient(h, A, 128, 0.0, 1, ctx=ctx)
+    assert ctx.launch_count() > 100 and ctx.last_steps == 2
+    e2 = T.energy(h, A, 128, 0.0, 1, ctx=ctx)
+    assert e2 == pytest.approx(e1, rel=1e-11)
+    assert abs(np.sum(g1 * A)) < 1e-9 * np.linalg.norm(g1)
+    for p in [(0, 3, 2, 1, 4), (2, 1, 0, 3, 4), (1, 0, 3, 2, 4), (3, 2, 1, 0, 4)]:
+        assert rel(np.transpose(g1, p), g1) < 1e-9        # gradient inherits the index-permutation symmetry

@@ -1,0 +1,222 @@
+"""CPU: host-side logic of the product -- the C-ABI library loads and exports every symbol of include/tnad.h,
+the einsum -> GEMM planner's stride algebra, the host mirror of the reference API, and the multi-process
+(gloo, world_size 2) plumbing of the replicated / sweep paths.  No compute call touches a GPU here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import tnad_b200 as T
+import tnad_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI -------------------------------------------------------------------------------------------
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "tnad.h")).read()
+    return sorted(set(re.findall(r"TNAD_API\s+[\w\s\*]+?\b(tnad_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = T.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tnad.h but not exported"
+    assert set(declared) == set(T.SIGNATURES), "ctypes binding table and header disagree"
+    assert lib.tnad_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    lib = T.load_library()
+    import ctypes as C
+    h = C.c_void_p()
+    rc = lib.tnad_create(99, C.byref(h))       # no such device anywhere
+    assert rc != 0 and not h.value
+    msg = lib.tnad_last_error(None).decode()
+    assert "device" in msg.lower()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tensornetworkad.jl_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "tnad_oracle" not in src and "oracle/" not in src, fn
+    for fn in os.listdir(os.path.join(pkg, "csrc")):
+        for line in open(os.path.join(pkg, "csrc", fn)):
+            if line.lstrip().startswith("#include"):
+                assert "oracle" not in line, (fn, line)
+
+
+# ---- einsum -> GEMM planner ------------------------------------------------------------------------------
+DRIVER_SPECS = """iba,ad->ibd ibd,dcl->ibcl ibcl,jkcb->ijlk pq,qj->pj pi,pj->ij abi,aed->ibed ibed,bjce->ijcd ijcd,dck->ijk
+pi,ij->pj pj,qj->pq qp,qj->pj ijk,dck->ijcd ijcd,ijk->dck ijcd,bjce->ibed ibed,ijcd->bjce ibed,aed->abi abi,ibed->aed
+ijlk,jkcb->ibcl ibcl,ijlk->jkcb ibcl,dcl->ibd ibd,ibcl->dcl ibd,ad->iba iba,ibd->ad
+ica,ab->icb eg,gfk->efk icb,bde->icde icde,cjfdlm->iejflm iejflm,efk->ijklm abckl,ijkl->abcij abcij,ij->abc abc,ij->abcij
+ijklm,efk->iejflm iejflm,ijklm->efk iejflm,cjfdlm->icde icde,iejflm->cjfdlm icde,bde->icb icb,icde->bde efk,gfk->eg
+eg,efk->gfk icb,ab->ica ica,icb->ab npu,por->nour dom,lmn->dlno nour,dlno->urdl urdl,dlno->nour nour,urdl->dlno
+nour,por->npu npu,nour->por dlno,lmn->dom dom,dlno->lmn mi,mj->ij ij,nj->in mi,in->mn mi,ij->mj mj,nj->mn mk,m->k mk,k->m
+ia,ajb->ijb ijb,bk->ijk alc,ckd->alkd bjd,bia->jdia alkd,jdia->ijkl mr,mq->rq mr,rq->mq ki,kj->ij ik,kj->ij""".split()
+
+
+def _off(levels, i):
+    o = 0
+    for l, (n, s) in enumerate(levels):
+        if l == len(levels) - 1:
+            o += i * s
+        else:
+            o += (i % n) * s
+            i //= n
+    return o
+
+
+def _run_plan(spec, A, B):
+    p = T.contract_plan(spec, A.shape, B.shape)
+    lhs, out = spec.split("->")
+    la, lb = lhs.split(",")
+    ext = dict(zip(la, A.shape)); ext.update(zip(lb, B.shape))
+    cshape = tuple(ext[l] for l in out)
+    Af, Bf = A.reshape(-1, order="F"), B.reshape(-1, order="F")
+    Cf = np.zeros(int(np.prod(cshape)))
+    am = np.array([_off(p["am"], i) for i in range(p["M"])]); cm = np.array([_off(p["cm"], i) for i in range(p["M"])])
+    ak = np.array([_off(p["ak"], i) for i in range(p["K"])]); bk = np.array([_off(p["bk"], i) for i in range(p["K"])])
+    bn = np.array([_off(p["bn"], i) for i in range(p["N"])]); cn = np.array([_off(p["cn"], i) for i in range(p["N"])])
+    for b in range(p["batch"]):
+        ab, bb, cb = _off(p["ab"], b), _off(p["bb"], b), _off(p["cb"], b)
+        Cf[cb + cm[:, None] + cn[None, :]] = Af[ab + am[:, None] + ak[None, :]] @ Bf[bb + bk[:, None] + bn[None, :]]
+    for vec, kfast, r, k in ((p["a_vec"], p["a_kfast"], p["am"], p["ak"]), (p["b_vec"], p["b_kfast"], p["bn"], p["bk"])):
+        if vec:
+            fast = k if kfast else r
+            assert fast[0][1] == 1 and fast[0][0] % 2 == 0
+    return Cf.reshape(cshape, order="F"), p
+
+
+@pytest.mark.parametrize("spec", DRIVER_SPECS)
+def test_contract_plan_matches_einsum(spec):
+    rng = np.random.default_rng(abs(hash(spec)) % 2 ** 32)
+    labs = sorted(set(re.sub("[^a-z]", "", spec)))
+    for trial in range(3):
+        ext = {l: int(rng.integers(1 if trial == 2 else 2, 7)) for l in labs}
+        lhs, _ = spec.split("->")
+        la, lb = lhs.split(",")
+        A = rng.standard_normal([ext[l] for l in la]); B = rng.standard_normal([ext[l] for l in lb])
+        C, p = _run_plan(spec, A, B)
+        assert np.allclose(C, np.einsum(spec, A, B), atol=1e-12)
+        for s in ("am", "ak", "bk", "bn", "cm", "cn"):
+            assert 1 <= len(p[s]) <= 4
+
+
+def test_contract_plan_headline_shapes_are_vectorised():
+    # d=4, chi=128: the big contractions must take the 16-byte cp.async path on both operands
+    chi, D = 128, 16
+    for spec, sa, sb in [("ibcl,jkcb->ijlk", (chi, D, D, chi), (D, D, D, D)), ("ibd,dcl->ibcl", (chi, D, chi), (chi, D, chi)),
+                         ("ibed,bjce->ijcd", (chi, D, D, chi), (D, D, D, D)), ("pq,qj->pj", (chi * D, chi * D), (chi * D, chi))]:
+        p = T.contract_plan(spec, sa, sb)
+        assert p["a_vec"] == 1 and p["b_vec"] == 1, spec
+
+
+def test_contract_plan_rejects_bad_specs():
+    with pytest.raises(T.TnadError):
+        T.contract_plan("ab,bc->ad", (2, 3), (3, 4))
+    with pytest.raises(T.TnadError):
+        T.contract_plan("ab,bc->ac", (2, 3), (4, 4))
+
+
+# ---- host mirror of the reference API ---------------------------------------------------------------------
+def test_model_builders_match_oracle():
+    for b in (0.2, 0.44, 0.9):
+        assert np.array_equal(T.model_tensor(T.Ising(), b), O.model_tensor_ising(b))
+        assert np.array_equal(T.mag_tensor(T.Ising(), b), O.mag_tensor_ising(b))
+        assert np.allclose(T.dmodel_tensor(T.Ising(), b), O.dmodel_tensor_ising(b), atol=1e-15)
+        assert T.magofbeta(T.Ising(), b) == O.magofbeta(b)
+    assert np.array_equal(T.hamiltonian(T.Heisenberg()), O.hamiltonian_heisenberg())
+    assert np.array_equal(T.hamiltonian(T.Heisenberg(2.0, 0.5, 0.5)), O.hamiltonian_heisenberg(2.0, 0.5, 0.5))
+    assert np.array_equal(T.hamiltonian(T.TFIsing(0.7)), O.hamiltonian_tfising(0.7))
+    assert np.array_equal(T.diaglocalhamiltonian([0.3, 0.1, -0.43]), O.diaglocalhamiltonian([0.3, 0.1, -0.43]))
+    assert np.allclose(T.tensorfromclassical([[0.3, -0.3], [-0.3, 0.3]]), T.model_tensor(T.Ising(), 0.3), atol=1e-14)
+
+
+def test_ipeps_types():
+    # test/ctmrg.jl:6-14
+    assert isinstance(T.SquareLattice(), T.AbstractLattice)
+    assert isinstance(T.IPEPS(np.random.randn(2, 3, 3, 3, 3)), T.IPEPS)
+    sq = T.SquareIPEPS(np.random.randn(3, 3, 3, 3, 2))
+    assert T.getd(sq) == 3 and T.gets(sq) == 2
+    with pytest.raises(T.DimensionMismatch):
+        T.SquareIPEPS(np.random.randn(3, 3, 4, 3, 2))
+    x = T.indexperm_symmetrize(sq).bulk
+    assert np.allclose(x, O.indexperm_symmetrize(sq.bulk)) and np.linalg.norm(x) == pytest.approx(1.0)
+    for p in [(0, 3, 2, 1, 4), (2, 1, 0, 3, 4), (1, 0, 3, 2, 4), (3, 2, 1, 0, 4)]:
+        assert np.allclose(x, np.transpose(x, p))
+
+
+def test_runtime_constructor_random_env():
+    rt = T.SquareCTMRGRuntime(np.random.randn(2, 2, 2, 2), "random", 10, rng=np.random.default_rng(0))
+    assert isinstance(rt, T.CTMRGRuntime) and T.getchi(rt) == 10 and T.getD(rt) == 2
+    assert np.allclose(rt.corner, rt.corner.T) and np.allclose(rt.edge, np.transpose(rt.edge, (2, 1, 0)))
+
+
+def test_fixedpoint_semantics():
+    # test/fixedpoint.jl:13-26
+    nxt = lambda g: 0.5 * (g + 9 / g)  # noqa: E731
+    assert T.fixedpoint(nxt, 9, lambda x: True) == 9
+
+    class Stop2:
+        def __init__(self):
+            self.c = 0
+
+        def __call__(self, v):
+            self.c += 1
+            return self.c == 2
+    assert T.fixedpoint(nxt, 9, Stop2()) == pytest.approx(0.5 * (9 + 1))
+    st = T.StopFunction(np.full(3, np.inf), -1, 0.0, 2)
+    n = 0
+    state = (None, np.full(3, np.inf))
+    while not st(state):
+        n += 1
+        state = (None, np.arange(3.0) + n)
+    assert n == 3                                     # counter from -1 => maxit + 1 applications
+
+
+def test_num_grad():
+    assert T.num_grad(lambda x: x * x, 3.0) == pytest.approx(6.0, rel=1e-6)
+    assert np.allclose(T.num_grad(np.trace, np.random.rand(2, 2)), np.eye(2), atol=1e-8)
+
+
+def test_argument_checks_raise_before_any_gpu_work():
+    c = T.Context.__new__(T.Context)            # no device needed: checks run in the Python layer first
+    with pytest.raises(T.DimensionMismatch):
+        T.Context.energy(c, np.zeros((2, 2, 2, 2)), np.zeros((2, 2, 3, 2, 2)), 4, 0.0, 1)
+    with pytest.raises(T.DimensionMismatch):
+        T.Context.trg_forward(c, np.zeros((2, 3, 3, 2)), 4, 1)
+
+
+# ---- N > 1 plumbing (gloo, world_size 2) ----------------------------------------------------------------------
+def test_gloo_world2_replica_plumbing(tmp_path):
+    script = tmp_path / "w2.py"
+    script.write_text(
+        "import os, sys, json\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "from tnad_b200.sweep import partition\n"
+        "d = bench.Dist(backend='gloo')\n"
+        "assert d.on and d.world == 2\n"
+        "mx = d.max(10.0 + d.rank); sm = d.sum(1.0 + d.rank)\n"
+        "mine = partition(7, d.rank, d.world)\n"
+        "d.barrier()\n"
+        f"open(os.path.join({str(tmp_path)!r}, 'r%d.json' % d.rank), 'w').write(json.dumps({{'rank': d.rank, 'max': mx, 'sum': sm, 'mine': mine}}))\n"
+        "d.close()\n")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    rows = [json.load(open(tmp_path / f"r{k}.json")) for k in range(2)]
+    assert all(x["max"] == 11.0 and x["sum"] == 3.0 for x in rows)
+    got = sorted(i for x in rows for i in x["mine"])
+    assert got == list(range(7))                      # every instance exactly once, no overlap
