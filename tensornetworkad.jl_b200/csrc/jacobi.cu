@@ -498,7 +498,7 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   double* fro2 = c->scal + 18;
   reduce(c, RED_SUMSQ, G, nullptr, fro2);
   const bool debug = env_int("TNAD_JACOBI_DEBUG", 0) != 0;
-  const int max_inner = env_int("TNAD_JACOBI_INNER", 4);
+  const int max_inner = env_int("TNAD_JACOBI_INNER", 1);
   const int max_sweeps = env_int("TNAD_JACOBI_SWEEPS", 60);
 
   SvdResult res;
