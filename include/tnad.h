@@ -88,6 +88,11 @@ TNAD_API int tnad_contract_plan(const char* spec, const int64_t* dimsA, int rank
 TNAD_API int tnad_svd(tnad_ctx* ctx, const double* A, int m, int n, double* U, double* S, double* V,
              int* sweeps_out /* may be NULL */);
 
+/* svd of a symmetric matrix as it occurs at ctmrg.jl:135-136 (cpmat + cpmat'): two-sided block Jacobi
+ * eigensolver, A = Q L Q' returned as U = Q, S = |L| (descending), V = Q sign(L).  A is symmetrised as
+ * (A + A')/2. */
+TNAD_API int tnad_svd_sym(tnad_ctx* ctx, const double* A, int n, double* U, double* S, double* V, int* sweeps_out);
+
 /* trg_svd(t, dmax, tol)  (trg.jl:33-44).  t is (d1,d2,d3,d4); u gets (d1,d2,k), v gets (k,d3,d4);
  * the buffers must hold dmax columns/rows; *k_out = kept rank. */
 TNAD_API int tnad_trg_svd(tnad_ctx* ctx, const double* t, int d1, int d2, int d3, int d4, int dmax, double tol,

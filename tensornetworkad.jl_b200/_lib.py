@@ -38,6 +38,7 @@ SIGNATURES = {
                                 C.c_int, C.c_double, C.c_double, C.c_void_p]),
     "tnad_contract_plan": (C.c_int, [C.c_char_p, c_int64_p, C.c_int, c_int64_p, C.c_int, c_int64_p]),
     "tnad_svd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
+    "tnad_svd_sym": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
     "tnad_trg_svd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                C.c_void_p, C.c_void_p, c_int_p]),
     "tnad_svd_back": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -244,6 +245,15 @@ class Context:
         U = np.empty((m, k), order="F"); S = np.empty(k); V = np.empty((n, k), order="F")
         sw = C.c_int(0)
         self.check(self.lib.tnad_svd(self.h, _p(A), m, n, _p(U), _p(S), _p(V), C.byref(sw)))
+        self.last_sweeps = sw.value
+        return U, S, V
+
+    def svd_sym(self, A):
+        A = farray(A)
+        n = A.shape[0]
+        U = np.empty((n, n), order="F"); S = np.empty(n); V = np.empty((n, n), order="F")
+        sw = C.c_int(0)
+        self.check(self.lib.tnad_svd_sym(self.h, _p(A), n, _p(U), _p(S), _p(V), C.byref(sw)))
         self.last_sweeps = sw.value
         return U, S, V
 

@@ -194,6 +194,18 @@ int tnad_svd(tnad_ctx* c, const double* A, int m, int n, double* U, double* S, d
   TNAD_API_END(c)
 }
 
+int tnad_svd_sym(tnad_ctx* c, const double* A, int n, double* U, double* S, double* V, int* sweeps_out) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(n >= 1, "tnad_svd_sym: empty matrix");
+  Tens tA = t_in(c, A, {n, n});
+  SvdResult r = svd_symmetric(c, tA, false);
+  t_out(c, r.U, U);
+  t_out(c, r.S, S);
+  t_out(c, r.V, V);
+  if (sweeps_out) *sweeps_out = r.sweeps;
+  TNAD_API_END(c)
+}
+
 int tnad_trg_svd(tnad_ctx* c, const double* t, int d1, int d2, int d3, int d4, int dmax, double tol, double* u,
                  double* v, int* k_out) {
   TNAD_API_BEGIN(c)

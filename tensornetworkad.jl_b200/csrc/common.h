@@ -228,4 +228,7 @@ struct SvdResult {
 // V0 (optional, n x n orthogonal): warm start for square inputs.
 SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false, const Tens* V0 = nullptr);
 
+// Symmetric input (ctmrg.jl:135-136): two-sided block Jacobi eigensolver, M = Q L Q' -> U = Q, S = |L|, V = Q sign(L).
+SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false);
+
 }  // namespace tnad

@@ -207,8 +207,13 @@ void ctmrg_step(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& e
   {
     Span s(c, 1);
     // svd(cpmat + cpmat') (ctmrg.jl:134-136); warm-started from the previous step's right vectors
-    svd = svd_jacobi(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);
-    if (Vwarm) *Vwarm = svd.V;
+    const char* se = getenv("TNAD_SYMEIG");
+    if (se && se[0] == '0') {
+      svd = svd_jacobi(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);   // one-sided path (A/B switch)
+      if (Vwarm) *Vwarm = svd.V;
+    } else {
+      svd = svd_symmetric(c, CP, true);
+    }
   }
   Tens Z = t_slice_last(svd.U, 0, chi);          // u[:, 1:chi]
   Tens z = t_reshape(Z, {chi, D, chi});           // (ctmrg.jl:137)

@@ -621,6 +621,19 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   return res;
 }
 
+// X[:, (I,J)] <- X[:, (I,J)] * W_pair for every pair of the round (X has ld rows in nchunks 128-row chunks)
+void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int p, int round, const double* Wbuf,
+                           const int* skip) {
+  static bool attr_set = false;
+  const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
+  if (!attr_set) {
+    TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
+    attr_set = true;
+  }
+  k_jacobi_update<<<dim3(p / 2, nchunks), 256, smem_upd, c->stream>>>(X, ld, nchunks, nullptr, 0, p, round, Wbuf, skip);
+  LAUNCH_CHECK(c);
+}
+
 SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* V0) {
   return svd_jacobi_impl(c, A, sym_add_transpose, 0, V0);
 }
