@@ -52,7 +52,16 @@ int tnad_create(int device, tnad_ctx** out) {
     c = new tnad_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    TNAD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // the main stream carries the latency-critical pivot kernels of the eigensolver: give it the highest
+    // priority so its CTAs are scheduled ahead of the bulk update kernels running on streams 2 and 3
+    int prio_lo = 0, prio_hi = 0;
+    TNAD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    TNAD_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+    TNAD_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+    TNAD_CUDA(cudaEventCreateWithFlags(&c->ev_eig, cudaEventDisableTiming));
+    TNAD_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
+    TNAD_CUDA(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_lo));
+    TNAD_CUDA(cudaEventCreateWithFlags(&c->ev_v, cudaEventDisableTiming));
     TNAD_CUDA(cudaMalloc((void**)&c->scal, SCAL_SLOTS * sizeof(double)));
     TNAD_CUDA(cudaMalloc((void**)&c->partial, PARTIAL_SLOTS * sizeof(double)));
     TNAD_CUDA(cudaMallocHost((void**)&c->hpin, HPIN_SLOTS * sizeof(double)));
@@ -79,6 +88,8 @@ int tnad_destroy(tnad_ctx* c) {
   if (!c) return TNAD_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  if (c->stream3) cudaStreamSynchronize(c->stream3);
   for (auto& s : c->spans) {
     cudaEventDestroy(s.second.first);
     cudaEventDestroy(s.second.second);
@@ -93,6 +104,12 @@ int tnad_destroy(tnad_ctx* c) {
   cudaFree(c->scal);
   cudaFree(c->partial);
   cudaFreeHost(c->hpin);
+  tnad::symeig_cache_free(c);
+  if (c->ev_eig) cudaEventDestroy(c->ev_eig);
+  if (c->ev_rest) cudaEventDestroy(c->ev_rest);
+  if (c->ev_v) cudaEventDestroy(c->ev_v);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
   cudaStreamDestroy(c->stream);
   delete c;
   return TNAD_OK;

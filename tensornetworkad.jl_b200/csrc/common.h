@@ -41,6 +41,10 @@ struct Error {
 struct tnad_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr, stream3 = nullptr;   // look-ahead streams of the symmetric eigensolver
+  cudaEvent_t ev_eig = nullptr, ev_rest = nullptr, ev_v = nullptr;
+  // cached workspace + captured one-sweep CUDA graph of the symmetric eigensolver, keyed by matrix size
+  struct SymEigCache* symcache = nullptr;
   std::string err;
   int pointer_mode = TNAD_POINTER_HOST;
   int64_t launches = 0;
@@ -141,7 +145,8 @@ struct KTimer {
   tnad_ctx* c;
   int fam;
   cudaEvent_t a = nullptr, b = nullptr;
-  KTimer(tnad_ctx* c, int fam);
+  cudaStream_t st = nullptr;
+  KTimer(tnad_ctx* c, int fam, cudaStream_t st = nullptr);
   ~KTimer();
 };
 cudaEvent_t get_event(tnad_ctx* c);
@@ -229,6 +234,7 @@ struct SvdResult {
 SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false, const Tens* V0 = nullptr);
 
 // Symmetric input (ctmrg.jl:135-136): two-sided block Jacobi eigensolver, M = Q L Q' -> U = Q, S = |L|, V = Q sign(L).
-SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false);
+SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false, const Tens* Q0 = nullptr);
+void symeig_cache_free(tnad_ctx* c);
 
 }  // namespace tnad

@@ -212,7 +212,8 @@ void ctmrg_step(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& e
       svd = svd_jacobi(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);   // one-sided path (A/B switch)
       if (Vwarm) *Vwarm = svd.V;
     } else {
-      svd = svd_symmetric(c, CP, true);
+      svd = svd_symmetric(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);
+      if (Vwarm) *Vwarm = svd.U;
     }
   }
   Tens Z = t_slice_last(svd.U, 0, chi);          // u[:, 1:chi]
@@ -273,7 +274,7 @@ int ctmrg_loop(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge, double t
   std::vector<double> oldvals(n, INFINITY);
   vals.assign(n, INFINITY);
   const char* wenv = getenv("TNAD_WARMSTART");
-  const bool warm = !(wenv && wenv[0] == '0');
+  const bool warm = (wenv && wenv[0] == '1');   // measured: no gain on the two-sided path (cluster-limited sweeps)
   Tens Vwarm;
   long long counter = -1;   // ctmrg.jl:114
   int nsteps = 0;

@@ -623,14 +623,14 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
 
 // X[:, (I,J)] <- X[:, (I,J)] * W_pair for every pair of the round (X has ld rows in nchunks 128-row chunks)
 void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int p, int round, const double* Wbuf,
-                           const int* skip) {
+                           const int* skip, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
     attr_set = true;
   }
-  k_jacobi_update<<<dim3(p / 2, nchunks), 256, smem_upd, c->stream>>>(X, ld, nchunks, nullptr, 0, p, round, Wbuf, skip);
+  k_jacobi_update<<<dim3(p / 2, nchunks), 256, smem_upd, st ? st : c->stream>>>(X, ld, nchunks, nullptr, 0, p, round, Wbuf, skip);
   LAUNCH_CHECK(c);
 }
 

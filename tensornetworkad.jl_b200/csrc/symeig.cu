@@ -24,7 +24,7 @@
 namespace tnad {
 
 void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int p, int round, const double* Wbuf,
-                           const int* skip);   // jacobi.cu
+                           const int* skip, cudaStream_t st);   // jacobi.cu
 
 namespace {
 
@@ -85,7 +85,7 @@ constexpr int ER = JP / EW;      // rows per warp
 
 __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ M, long long ld, int p, int round,
                                                      int nreal, const double* __restrict__ fro2, double tolfac,
-                                                     int max_inner, double* __restrict__ Wbuf,
+                                                     int max_inner, int cross, double* __restrict__ Wbuf,
                                                      int* __restrict__ skip,
                                                      unsigned long long* __restrict__ offmax_bits) {
   __shared__ double Ps[JP * HLD];
@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ 
   int buf = 0;
   for (int sw = 0; sw < max_inner; ++sw) {
     int rotated = 0;
-    for (int step = 0; step < JP - 1; ++step) {
+    // cross mode: only the 32 x 32 pairs (column of block I, column of block J) are rotated -- tops stay, bottoms
+    // rotate through the lanes (one shuffle per value, 32 steps).  The within-block pairs are rotated once per
+    // sweep by the full schedule (63 Brent-Luk steps) of the sweep's first round: every element pair of M is
+    // then visited exactly once per sweep, as in the classical cyclic-by-blocks Jacobi method.
+    const int nsteps = cross ? JB : JP - 1;
+    for (int step = 0; step < nsteps; ++step) {
       double app = 0.0, aqq = 0.0, apq = 0.0;
 #pragma unroll
       for (int i = 0; i < ER; ++i) {
@@ -172,6 +177,15 @@ __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ 
           wt[i] = c * e - s * f;
           wb[i] = s * e + c * f;
         }
+      }
+      if (cross) {
+#pragma unroll
+        for (int i = 0; i < ER; ++i) {
+          yb[i] = __shfl_sync(0xffffffffu, yb[i], (k + 1) & 31);
+          wb[i] = __shfl_sync(0xffffffffu, wb[i], (k + 1) & 31);
+        }
+        ob = __shfl_sync(0xffffffffu, ob, (k + 1) & 31);
+        continue;
       }
       // Brent-Luk move: top_0 stays, top_1 <- bot_0, top_k <- top_{k-1}, bot_k <- bot_{k+1}, bot_31 <- top_31
 #pragma unroll
@@ -243,10 +257,22 @@ __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ 
 }
 
 // ---- 2. fused two-sided update of M ------------------------------------------------------------------------
+// mode 0: every block (a <= b); mode 1: only the blocks in `plist` (those that contain next round's pivot
+// blocks, so the next k_sym_eig can start early); mode 2: every block not flagged in `prio`.
 __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, long long ld, int p, int round,
-                                                      const double* __restrict__ Wbuf, const int* __restrict__ skip) {
-  const int a = blockIdx.x, b = blockIdx.y;
-  if (b < a) return;
+                                                      const double* __restrict__ Wbuf, const int* __restrict__ skip,
+                                                      int mode, const int* __restrict__ plist,
+                                                      const unsigned char* __restrict__ prio, int npairs) {
+  int a, b;
+  if (mode == 1) {
+    a = plist[2 * blockIdx.x];
+    b = plist[2 * blockIdx.x + 1];
+  } else {
+    a = blockIdx.x;
+    b = blockIdx.y;
+    if (b < a) return;
+    if (mode == 2 && prio[a * npairs + b]) return;
+  }
   const int ska = skip[a], skb = skip[b];
   if (ska && skb) return;
   extern __shared__ __align__(16) double sm[];
@@ -384,6 +410,16 @@ __global__ void k_sym_finalize(const double* __restrict__ Q, long long ldq, cons
 
 __global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
 
+// E = 1.5 I - 0.5 T in place (Newton-Schulz polish of a warm-start basis)
+__global__ void k_ns_factor(double* T, long long n) {
+  const long long total = n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx % n, j = idx / n;
+    T[idx] = (i == j ? 1.5 : 0.0) - 0.5 * T[idx];
+  }
+}
+
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -391,69 +427,247 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+}  // namespace tnad
+
+// Per-context cache: work buffers, look-ahead tables and the captured one-sweep CUDA graph, keyed by n.
+struct SymEigCache {
+  int64_t n = -1;
+  int max_inner = 0;
+  tnad::Tens Mw, Q, Wbuf, Wbuf2, skipbuf, skipbuf2, tabbuf, plbuf;
+  std::vector<int> pcount;
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0;
+};
+
+namespace tnad {
+
+void symeig_cache_free(tnad_ctx* c) {
+  if (!c->symcache) return;
+  if (c->symcache->exec) cudaGraphExecDestroy(c->symcache->exec);
+  delete c->symcache;
+  c->symcache = nullptr;
+}
+
 // SVD of the symmetric matrix A (+ A^T when `sym_add_transpose`) through its eigen-decomposition.
-SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
+SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* Q0) {
   TNAD_REQUIRE(A.rank == 2 && A.dim[0] == A.dim[1], "svd_symmetric: need a square matrix");
   const int64_t n = A.dim[0];
   const int64_t N = (n + JP - 1) / JP * JP;
-  const int p = (int)(N / JB), npairs = p / 2;
+  const int p = (int)(N / JB), npairs = p / 2, nr = p - 1;
   const int chunks = (int)((N + 127) / 128);
   const int64_t ld = (int64_t)chunks * 128;   // rows padded to the 128-row chunks of the panel kernel
-
-  static bool attr_set = false;
   const size_t smem_upd = (size_t)(3 * JP * BLD) * sizeof(double);
+  static bool attr_set = false;
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_sym_update_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
     attr_set = true;
   }
-  Tens Mw = t_alloc(c, {ld, N}, true);
-  Tens Q = t_alloc(c, {ld, N}, false);
-  {
-    const long long total = n * n;
-    int nb = (int)std::min<long long>((total + 1023) / 1024, 148 * 8);
-    k_load_sym<<<nb < 1 ? 1 : nb, 256, 0, c->stream>>>(Mw.p, ld, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
-    LAUNCH_CHECK(c);
-  }
-  set_identity(c, Q.p, ld, N);
-  double* fro2 = c->scal + 18;
-  reduce(c, RED_SUMSQ, Mw, nullptr, fro2);
-  Tens Wbuf = t_alloc(c, {(int64_t)JP * JP, (int64_t)npairs});
-  Tens skipbuf = t_alloc(c, {(int64_t)npairs + 2});
-  int* skip = reinterpret_cast<int*>(skipbuf.p);
-  unsigned long long* offbits = reinterpret_cast<unsigned long long*>(c->scal + 16);
-
   const double eps = 2.220446049250313e-16;
   const double tolfac = 16.0 * eps;   // |m_pq| <= 16 eps |M|_F  (LAPACK-class absolute accuracy)
   const bool debug = env_int("TNAD_JACOBI_DEBUG", 0) != 0;
   const int max_inner = env_int("TNAD_SYMEIG_INNER", 1);
   const int max_sweeps = env_int("TNAD_JACOBI_SWEEPS", 60);
+  const bool lookahead = env_int("TNAD_LOOKAHEAD", 1) != 0 && npairs >= 4;
+  const bool use_graph = env_int("TNAD_GRAPH", 1) != 0 && !c->ktiming;
+  const bool cross_mode = env_int("TNAD_SYMEIG_CROSS", 1) != 0;
+  double* fro2 = c->scal + 18;
+  unsigned long long* offbits = reinterpret_cast<unsigned long long*>(c->scal + 16);
+  cudaStream_t S1 = c->stream, S2 = c->stream2, S3 = env_int("TNAD_S3", 0) ? c->stream3 : c->stream2;
+
+  // ---- cached workspace ------------------------------------------------------------------------------------
+  if (!c->symcache || c->symcache->n != n || c->symcache->max_inner != max_inner + (cross_mode ? 100 : 0)) {
+    symeig_cache_free(c);
+    SymEigCache* sc = new SymEigCache();
+    c->symcache = sc;
+    sc->n = n;
+    sc->max_inner = max_inner + (cross_mode ? 100 : 0);
+    sc->Mw = t_alloc(c, {ld, N});
+    sc->Q = t_alloc(c, {ld, N});
+    sc->Wbuf = t_alloc(c, {(int64_t)JP * JP, (int64_t)npairs});
+    sc->Wbuf2 = t_alloc(c, {(int64_t)JP * JP, (int64_t)npairs});
+    sc->skipbuf = t_alloc(c, {(int64_t)npairs + 2});
+    sc->skipbuf2 = t_alloc(c, {(int64_t)npairs + 2});
+    // look-ahead tables: the pivot blocks of round r+1 live in a few blocks of the round-r update ("priority"
+    // blocks: the npairs diagonal blocks plus one cross block per next pair).
+    std::vector<unsigned char> prio_h((size_t)nr * npairs * npairs + 8, 0);
+    std::vector<int> plist_h((size_t)nr * 2 * npairs * 2 + 8, 0);
+    sc->pcount.assign((size_t)nr, 0);
+    std::vector<int> pair_of((size_t)p);
+    for (int r = 0; r < nr; ++r) {
+      for (int k = 0; k < npairs; ++k) {
+        int I, J;
+        rr_pair(p, r, k, I, J);
+        pair_of[I] = k;
+        pair_of[J] = k;
+      }
+      unsigned char* tab = prio_h.data() + (size_t)r * npairs * npairs;
+      for (int k = 0; k < npairs; ++k) tab[k * npairs + k] = 1;
+      const int rn = (r + 1) % nr;
+      for (int k = 0; k < npairs; ++k) {
+        int I, J;
+        rr_pair(p, rn, k, I, J);
+        const int a = std::min(pair_of[I], pair_of[J]), b = std::max(pair_of[I], pair_of[J]);
+        tab[a * npairs + b] = 1;
+      }
+      int cnt = 0;
+      int* pl = plist_h.data() + (size_t)r * 2 * npairs * 2;
+      for (int a = 0; a < npairs; ++a)
+        for (int b = a; b < npairs; ++b)
+          if (tab[a * npairs + b]) {
+            pl[2 * cnt] = a;
+            pl[2 * cnt + 1] = b;
+            ++cnt;
+          }
+      sc->pcount[r] = cnt;
+    }
+    sc->tabbuf = t_alloc(c, {(int64_t)(prio_h.size() / 8 + 2)});
+    sc->plbuf = t_alloc(c, {(int64_t)(plist_h.size() / 2 + 2)});
+    TNAD_CUDA(cudaMemcpyAsync(sc->tabbuf.p, prio_h.data(), prio_h.size(), cudaMemcpyHostToDevice, S1));
+    TNAD_CUDA(cudaMemcpyAsync(sc->plbuf.p, plist_h.data(), plist_h.size() * sizeof(int), cudaMemcpyHostToDevice, S1));
+    sync(c);
+  }
+  SymEigCache* sc = c->symcache;
+  Tens& Mw = sc->Mw;
+  Tens& Q = sc->Q;
+  double* Wb[2] = {sc->Wbuf.p, sc->Wbuf2.p};
+  int* sk[2] = {reinterpret_cast<int*>(sc->skipbuf.p), reinterpret_cast<int*>(sc->skipbuf2.p)};
+  const unsigned char* prio_d = reinterpret_cast<const unsigned char*>(sc->tabbuf.p);
+  const int* plist_d = reinterpret_cast<const int*>(sc->plbuf.p);
+
+  TNAD_CUDA(cudaMemsetAsync(Mw.p, 0, (size_t)(ld * N) * sizeof(double), S1));
+  const long long total_nn = n * n;
+  const int nb_nn = (int)std::max<long long>(1, std::min<long long>((total_nn + 1023) / 1024, 148 * 8));
+  set_identity(c, Q.p, ld, N);
+  if (Q0 && Q0->rank == 2 && Q0->dim[0] == n && Q0->dim[1] == n) {
+    // Warm start (successive CTMRG steps have nearly the same eigenvectors): M' = Q0' M Q0 is already close
+    // to diagonal, so only the quadratically convergent tail of the Jacobi iteration is left to do.  Q0 is
+    // re-orthogonalised (Newton-Schulz) first, so orthogonality errors do not accumulate across steps.
+    Tens Ms = t_alloc(c, {n, n});
+    k_load_sym<<<nb_nn, 256, 0, S1>>>(Ms.p, n, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
+    LAUNCH_CHECK(c);
+    Tens T = contract_new(c, "ki,kj->ij", *Q0, *Q0);
+    k_ns_factor<<<nb_nn, 256, 0, S1>>>(T.p, n);
+    LAUNCH_CHECK(c);
+    Tens Qv = t_wrap(Q.p, {n, n});
+    Qv.str[1] = ld;
+    contract(c, "ik,kj->ij", *Q0, T, Qv, 1.0, 0.0);
+    Tens T1 = contract_new(c, "ik,kj->ij", Ms, Qv);
+    Tens Mp = contract_new(c, "ki,kj->ij", Qv, T1);
+    k_load_sym<<<nb_nn, 256, 0, S1>>>(Mw.p, ld, Mp.p, 1, n, n, 0);   // exact symmetrisation (M' + M'^T)/2
+    LAUNCH_CHECK(c);
+  } else {
+    k_load_sym<<<nb_nn, 256, 0, S1>>>(Mw.p, ld, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
+    LAUNCH_CHECK(c);
+  }
+  {
+    Tens Mflat = t_wrap(Mw.p, {ld * N});
+    reduce(c, RED_SUMSQ, Mflat, nullptr, fro2);
+  }
   double fro2h;
   d2h(c, &fro2h, fro2, 1);
   const double tol = tolfac * std::sqrt(fro2h);
+
+  // ---- one sweep: all rounds, two streams -------------------------------------------------------------------
+  // Stream 1 runs  eig_r -> priority-update_r -> eig_{r+1};  stream 2 runs the rest of update_r and the Q update
+  // behind it, so the latency-bound pivot kernel (32 SMs) overlaps with the DMMA updates on the other SMs.
+  int nodes = 0;
+  auto issue_sweep = [&]() {
+    nodes = 0;
+    k_set_u64<<<1, 1, 0, S1>>>(offbits, 0ULL);
+    ++nodes;
+    if (!lookahead) {
+      for (int r = 0; r < nr; ++r) {
+        {
+          KTimer kt(c, KF_EIG);
+          k_sym_eig<<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, r, (int)n, fro2, tolfac, max_inner, (cross_mode && r > 0) ? 1 : 0, Wb[0], sk[0],
+                                               offbits);
+        }
+        {
+          KTimer kt(c, KF_GRAM);
+          k_sym_update_m<<<dim3(npairs, npairs), 256, smem_upd, S1>>>(Mw.p, ld, p, r, Wb[0], sk[0], 0, nullptr, nullptr,
+                                                                     npairs);
+        }
+        {
+          KTimer kt(c, KF_UPDATE);
+          jacobi_rotate_columns(c, Q.p, ld, chunks, p, r, Wb[0], sk[0], S1);
+          c->launches--;
+        }
+        nodes += 3;
+      }
+      return;
+    }
+    {
+      KTimer kt(c, KF_EIG);
+      k_sym_eig<<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, 0, (int)n, fro2, tolfac, max_inner, 0, Wb[0], sk[0], offbits);
+    }
+    ++nodes;
+    for (int r = 0; r < nr; ++r) {
+      const int cur = r & 1;
+      TNAD_CUDA(cudaEventRecord(c->ev_eig, S1));
+      if (r > 0) {
+        TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_rest, 0));   // M fully updated by round r-1
+        TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_v, 0));      // W[cur^1] no longer read by the Q update of round r-1
+      }
+      {
+        KTimer kt(c, KF_GRAM);
+        k_sym_update_m<<<sc->pcount[r], 256, smem_upd, S1>>>(Mw.p, ld, p, r, Wb[cur], sk[cur], 1,
+                                                             plist_d + (size_t)r * 2 * npairs * 2,
+                                                             prio_d + (size_t)r * npairs * npairs, npairs);
+      }
+      TNAD_CUDA(cudaStreamWaitEvent(S2, c->ev_eig, 0));
+      {
+        KTimer kt(c, KF_GRAM, S2);
+        k_sym_update_m<<<dim3(npairs, npairs), 256, smem_upd, S2>>>(Mw.p, ld, p, r, Wb[cur], sk[cur], 2, nullptr,
+                                                                   prio_d + (size_t)r * npairs * npairs, npairs);
+      }
+      TNAD_CUDA(cudaEventRecord(c->ev_rest, S2));
+      TNAD_CUDA(cudaStreamWaitEvent(S3, c->ev_eig, 0));
+      {
+        KTimer kt(c, KF_UPDATE, S3);
+        jacobi_rotate_columns(c, Q.p, ld, chunks, p, r, Wb[cur], sk[cur], S3);
+        c->launches--;
+      }
+      TNAD_CUDA(cudaEventRecord(c->ev_v, S3));
+      nodes += 3;
+      if (r + 1 < nr) {
+        KTimer kt(c, KF_EIG);
+        k_sym_eig<<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, r + 1, (int)n, fro2, tolfac, max_inner, cross_mode ? 1 : 0,
+                                             Wb[cur ^ 1], sk[cur ^ 1], offbits);
+        ++nodes;
+      }
+    }
+    TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_rest, 0));
+    TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_v, 0));
+  };
+
+  if (use_graph && !sc->exec) {
+    cudaGraph_t graph = nullptr;
+    TNAD_CUDA(cudaStreamBeginCapture(S1, cudaStreamCaptureModeThreadLocal));
+    try {
+      issue_sweep();
+    } catch (...) {
+      cudaStreamEndCapture(S1, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    TNAD_CUDA(cudaStreamEndCapture(S1, &graph));
+    TNAD_CUDA(cudaGraphInstantiate(&sc->exec, graph, 0));
+    cudaGraphDestroy(graph);
+    sc->nodes = nodes;
+  }
 
   SvdResult res;
   int sweep = 0;
   bool converged = fro2h == 0.0;
   double prev_off = 1e300;
   for (; !converged && sweep < max_sweeps; ++sweep) {
-    k_set_u64<<<1, 1, 0, c->stream>>>(offbits, 0ULL);
-    LAUNCH_CHECK(c);
-    for (int r = 0; r < p - 1; ++r) {
-      {
-        KTimer kt(c, KF_EIG);
-        k_sym_eig<<<npairs, EW * 32, 0, c->stream>>>(Mw.p, ld, p, r, (int)n, fro2, tolfac, max_inner, Wbuf.p, skip,
-                                                       offbits);
-      }
-      LAUNCH_CHECK(c);
-      {
-        KTimer kt(c, KF_GRAM);
-        k_sym_update_m<<<dim3(npairs, npairs), 256, smem_upd, c->stream>>>(Mw.p, ld, p, r, Wbuf.p, skip);
-      }
-      LAUNCH_CHECK(c);
-      {
-        KTimer kt(c, KF_UPDATE);
-        jacobi_rotate_columns(c, Q.p, ld, chunks, p, r, Wbuf.p, skip);
-      }
+    if (use_graph) {
+      TNAD_CUDA(cudaGraphLaunch(sc->exec, S1));
+      c->launches += sc->nodes;
+    } else {
+      issue_sweep();
+      c->launches += nodes;
+      TNAD_CUDA(cudaGetLastError());
     }
     double off;
     d2h(c, &off, c->scal + 16, 1);

@@ -141,15 +141,15 @@ cudaEvent_t get_event(tnad_ctx* c) {
   return e;
 }
 
-KTimer::KTimer(tnad_ctx* c_, int fam_) : c(c_), fam(fam_) {
+KTimer::KTimer(tnad_ctx* c_, int fam_, cudaStream_t st_) : c(c_), fam(fam_), st(st_ ? st_ : c_->stream) {
   if (!c->ktiming) return;
   a = get_event(c);
   b = get_event(c);
-  cudaEventRecord(a, c->stream);
+  cudaEventRecord(a, st);
 }
 KTimer::~KTimer() {
   if (!a) return;
-  cudaEventRecord(b, c->stream);
+  cudaEventRecord(b, st);
   c->kspans.push_back({fam, a, b});
 }
 
