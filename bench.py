@@ -239,23 +239,38 @@ def run_ours(args):
         ctx.set_kernel_timing(False)
         dmma_peak = ctx.dmma_peak()
         gemm_tf = ctx.gemm_bench(4096, 4096, 4096, 3)
-        n = CHI * d * d
-        npad = (n + 63) // 64 * 64
-        rows = ((n + 127) // 128 * 128) * 2           # G rows + V rows
-        fam = max(("jacobi_gram", "jacobi_eig", "jacobi_update", "gemm"), key=lambda k: kt[k]["ms"])
-        upd = kt["jacobi_update"]
-        # k_jacobi_update: [G;V][:, pair] <- [G;V][:, pair] * W for N/64 pairs: 2 * rows * 64 * 64 flops per pair
-        flops_per_launch = 2.0 * rows * 64 * 64 * (npad // 64)
-        achieved = flops_per_launch * upd["launches"] / (upd["ms"] * 1e-3) / 1e12 if upd["ms"] > 0 else 0.0
+        # executed work is counted on the device (skipped, already-converged pairs do no work), so the flop
+        # numerators below are exact: one k_sym_update_m block = two 64^3 products, one k_jacobi_update slab =
+        # one 128x64x64 product; the pivot kernel is FP64 vector math (dots + plane rotations).
+        mu, qu, pe = kt["m_update"], kt["q_update"], kt["pivot_eig"]
+        fl_m = mu.get("blocks", 0) * 2 * 2.0 * 64 ** 3
+        fl_q = qu.get("slabs", 0) * 2.0 * 128 * 64 * 64
+        tf_m = fl_m / (mu["ms"] * 1e-3) / 1e12 if mu["ms"] > 0 else 0.0
+        tf_q = fl_q / (qu["ms"] * 1e-3) / 1e12 if qu["ms"] > 0 else 0.0
         pk, pk_kind = peaks()
-        roof = {"bound": "tensor", "kernel": "k_jacobi_update (FP64 DMMA panel rotation of the block-Jacobi SVD)",
-                "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak else None,
-                "traffic": None,
-                "peak_source": "FP64 DMMA issue-rate microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure; "
-                               f"its hbm_gbs={pk.get('hbm_gbs')} [{pk_kind}] bounds the elementwise kernels)",
-                "kernel_families_ms": {k: round(v["ms"], 3) for k, v in kt.items()},
-                "kernel_families_launches": {k: v["launches"] for k, v in kt.items()},
-                "dominant_family": fam, "contraction_gemm_4096_tflops": gemm_tf}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("k_sym_update_m_dram_bytes_per_launch")
+        dom = max(("m_update", "pivot_eig", "q_update", "gemm"), key=lambda k: kt[k]["ms"])
+        roof = {"bound": "tensor",
+                "kernel": "k_sym_update_m (fused two-sided 64x64 block update M <- W'MW of the symmetric block-Jacobi "
+                          "eigensolver, FP64 DMMA m8n8k4)",
+                "achieved": tf_m, "peak": dmma_peak, "unit": "TFLOP/s", "frac": tf_m / dmma_peak if dmma_peak else None,
+                "traffic": traffic,
+                "flops_per_launch": fl_m / mu["launches"] if mu["launches"] else None,
+                "avg_launch_us": 1e3 * mu["ms"] / mu["launches"] if mu["launches"] else None,
+                "peak_source": "FP64 DMMA issue-rate microbenchmark (tnad_dmma_peak) run in this process: MEASURED_PEAKS.json "
+                               f"carries no FP64 figure (its hbm_gbs={pk.get('hbm_gbs')} [{pk_kind}] bounds the elementwise kernels)",
+                "kernel_ms_instrumented_pass": {k: round(v["ms"], 3) for k, v in kt.items()},
+                "kernel_launches": {k: v["launches"] for k, v in kt.items()},
+                "largest_family_by_device_time": dom,
+                "other_kernels": {
+                    "k_jacobi_update (Q <- Q W panel rotation, FP64 DMMA)": {"achieved_tflops": tf_q, "frac": tf_q / dmma_peak if dmma_peak else None},
+                    "k_sym_eig (64x64 pivot eigenproblem, register-resident Jacobi, FP64 vector + shuffles; latency bound, "
+                    "runs on N/64 SMs concurrently with the DMMA updates)": {"ms": round(pe["ms"], 3), "launches": pe["launches"]},
+                    "gemm_dmma_kernel (einsum contractions) on 4096^3": {"achieved_tflops": gemm_tf, "frac": gemm_tf / dmma_peak if dmma_peak else None}}}
         # -- CPU baseline on a bounded sample (same box, same run)
         if args.no_cpu_baseline:
             cpu = None

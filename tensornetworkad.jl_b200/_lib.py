@@ -177,8 +177,11 @@ class Context:
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()
         self.check(self.lib.tnad_kernel_timing(self.h, ms, cnt))
-        names = ["jacobi_gram", "jacobi_eig", "jacobi_update", "gemm", "other"]
-        return {n: dict(ms=ms[i], launches=int(cnt[i])) for i, n in enumerate(names)}
+        names = ["m_update", "pivot_eig", "q_update", "gemm", "other"]
+        out = {n: dict(ms=ms[i], launches=int(cnt[i])) for i, n in enumerate(names)}
+        out["m_update"]["blocks"] = int(cnt[5])     # executed 64x64 two-sided block updates (2 x 2*64^3 flop each)
+        out["q_update"]["slabs"] = int(cnt[6])      # executed 128x64 panel rotations (2*128*64*64 flop each)
+        return out
 
     def dmma_peak(self) -> float:
         t = C.c_double(0.0)

@@ -265,12 +265,14 @@ __global__ void __launch_bounds__(512) k_jacobi_eig(const double* __restrict__ H
 // ---- 3. rotate the column pair of G and V -------------------------------------------------------
 __global__ void __launch_bounds__(256) k_jacobi_update(double* __restrict__ G, long long ldg, int mchunks,
                                                        double* __restrict__ V, long long ldv, int p, int round,
-                                                       const double* __restrict__ Wbuf, const int* __restrict__ skip) {
+                                                       const double* __restrict__ Wbuf, const int* __restrict__ skip,
+                                                       unsigned long long* work_counter) {
   extern __shared__ __align__(16) double sm[];
   double* Xs = sm;
   double* Ws = sm + JP * XLD;
   const int pair = blockIdx.x, tid = threadIdx.x;
   if (skip[pair]) return;
+  if (work_counter && tid == 0) atomicAdd(work_counter, 1ULL);   // executed slabs (roofline accounting)
   int I, J;
   rr_pair(p, round, pair, I, J);
   const int cI = I * JB, cJ = J * JB;
@@ -523,7 +525,7 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
       {
       KTimer kt(c, KF_UPDATE);
       k_jacobi_update<<<dim3(npairs, mchunks + vchunks), 256, smem_upd, c->stream>>>(G.p, mpad, mchunks, Vw.p, ldv, p,
-                                                                                     r, Wbuf.p, skip);
+                                                                                     r, Wbuf.p, skip, c->ktiming ? reinterpret_cast<unsigned long long*>(c->scal + 21) : nullptr);
       }
       LAUNCH_CHECK(c);
     }
@@ -630,7 +632,8 @@ void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int 
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
     attr_set = true;
   }
-  k_jacobi_update<<<dim3(p / 2, nchunks), 256, smem_upd, st ? st : c->stream>>>(X, ld, nchunks, nullptr, 0, p, round, Wbuf, skip);
+  k_jacobi_update<<<dim3(p / 2, nchunks), 256, smem_upd, st ? st : c->stream>>>(X, ld, nchunks, nullptr, 0, p, round, Wbuf, skip,
+      c->ktiming ? reinterpret_cast<unsigned long long*>(c->scal + 21) : nullptr);
   LAUNCH_CHECK(c);
 }
 

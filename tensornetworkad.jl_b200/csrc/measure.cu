@@ -92,6 +92,8 @@ int tnad_set_kernel_timing(tnad_ctx* c, int enable) {
   }
   c->kspans.clear();
   c->ktiming = enable != 0;
+  TNAD_CUDA(cudaMemsetAsync(c->scal + 20, 0, 2 * sizeof(double), c->stream));
+  sync(c);
   API_END(c)
 }
 
@@ -110,6 +112,12 @@ int tnad_kernel_timing(tnad_ctx* c, double* ms, int64_t* count) {
       count[k.fam] += 1;
     }
   }
+  // executed work units of the DMMA update kernels: [5] 64x64 blocks of k_sym_update_m, [6] 128x64 slabs of k_jacobi_update
+  unsigned long long wc[2] = {0, 0};
+  TNAD_CUDA(cudaMemcpyAsync(wc, c->scal + 20, sizeof(wc), cudaMemcpyDeviceToHost, c->stream));
+  sync(c);
+  count[5] = (int64_t)wc[0];
+  count[6] = (int64_t)wc[1];
   API_END(c)
 }
 

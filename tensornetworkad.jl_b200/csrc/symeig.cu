@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ 
 __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, long long ld, int p, int round,
                                                       const double* __restrict__ Wbuf, const int* __restrict__ skip,
                                                       int mode, const int* __restrict__ plist,
-                                                      const unsigned char* __restrict__ prio, int npairs) {
+                                                      const unsigned char* __restrict__ prio, int npairs,
+                                                      unsigned long long* work_counter) {
   int a, b;
   if (mode == 1) {
     a = plist[2 * blockIdx.x];
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, lo
   }
   const int ska = skip[a], skb = skip[b];
   if (ska && skb) return;
+  if (work_counter && threadIdx.x == 0) atomicAdd(work_counter, 1ULL);   // executed blocks (roofline accounting)
   extern __shared__ __align__(16) double sm[];
   double* Xs = sm;                 // B, then T = Wa' B, then B' = T Wb; stored [col * BLD + row]
   double* Was = Xs + JP * BLD;     // W_a column-major: Was[i * BLD + k] = W_a[k][i]
@@ -570,6 +572,7 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
   // ---- one sweep: all rounds, two streams -------------------------------------------------------------------
   // Stream 1 runs  eig_r -> priority-update_r -> eig_{r+1};  stream 2 runs the rest of update_r and the Q update
   // behind it, so the latency-bound pivot kernel (32 SMs) overlaps with the DMMA updates on the other SMs.
+  unsigned long long* wc_m = c->ktiming ? reinterpret_cast<unsigned long long*>(c->scal + 20) : nullptr;
   int nodes = 0;
   auto issue_sweep = [&]() {
     nodes = 0;
@@ -585,7 +588,7 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
         {
           KTimer kt(c, KF_GRAM);
           k_sym_update_m<<<dim3(npairs, npairs), 256, smem_upd, S1>>>(Mw.p, ld, p, r, Wb[0], sk[0], 0, nullptr, nullptr,
-                                                                     npairs);
+                                                                     npairs, wc_m);
         }
         {
           KTimer kt(c, KF_UPDATE);
@@ -612,13 +615,13 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
         KTimer kt(c, KF_GRAM);
         k_sym_update_m<<<sc->pcount[r], 256, smem_upd, S1>>>(Mw.p, ld, p, r, Wb[cur], sk[cur], 1,
                                                              plist_d + (size_t)r * 2 * npairs * 2,
-                                                             prio_d + (size_t)r * npairs * npairs, npairs);
+                                                             prio_d + (size_t)r * npairs * npairs, npairs, wc_m);
       }
       TNAD_CUDA(cudaStreamWaitEvent(S2, c->ev_eig, 0));
       {
         KTimer kt(c, KF_GRAM, S2);
         k_sym_update_m<<<dim3(npairs, npairs), 256, smem_upd, S2>>>(Mw.p, ld, p, r, Wb[cur], sk[cur], 2, nullptr,
-                                                                   prio_d + (size_t)r * npairs * npairs, npairs);
+                                                                   prio_d + (size_t)r * npairs * npairs, npairs, wc_m);
       }
       TNAD_CUDA(cudaEventRecord(c->ev_rest, S2));
       TNAD_CUDA(cudaStreamWaitEvent(S3, c->ev_eig, 0));
