@@ -170,6 +170,8 @@ struct GemmDesc {
   double* C;
   double alpha, beta;
   int a_kfast, b_kfast, a_vec, b_vec;
+  int splitk;      // > 1: K is split over blockIdx.z, partial tiles go to ws
+  double* ws;
 };
 void gemm_run(tnad_ctx* c, const GemmDesc& d);
 

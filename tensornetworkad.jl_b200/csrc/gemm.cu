@@ -13,6 +13,7 @@
 // Operand tiles are kept in shared memory in the orientation they have in global memory
 // (k-fast or row-fast) with a +4 double pad, which makes every fragment load bank-conflict free.
 #include "common.h"
+#include <algorithm>
 
 namespace tnad {
 
@@ -60,40 +61,41 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
       : "d"(a), "d"(b));
 }
 
+// Out-of-line copy for set-up / epilogue code: keeps the integer divisions out of the unrolled main loop
+// (the first version inlined them into every tile load and stalled on instruction fetch -- ncu: 35-60 % of
+// issue slots lost to `no_instruction`).
+__device__ __noinline__ long long lvl_off_ni(const LvlSet& L, int i) { return lvl_off(L, i); }
+
 // Load one BR x BK operand tile (R = the M side of A or the N side of B) into shared memory.
 //   KF == true : shared layout s[r * (BK+4) + k]   (global memory is contiguous along k)
 //   KF == false: shared layout s[k * (BR+4) + r]   (global memory is contiguous along r)
-// rowoff[r] holds the global offset of row r0+r, or -1 when the row is out of range.
+// rowoff[r]: global offset of row r0+r (-1: out of range); kof[kl]: offset of k index kl of this tile (-1: past K).
 template <int BR, int NT, bool KF>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, const long long* rowoff,
-                                          const LvlSet& Lk, int k0, int K, bool vec, int tid) {
+                                          const long long* kof, bool vec, int tid) {
   if (KF) {
     constexpr int LD = BK + 4;
     if (vec) {
       constexpr int CPR = BK / 2;                 // 16-byte chunks per row
       constexpr int ITER = BR * CPR / NT;
       const int k2 = tid % CPR;
-      const int k = k0 + 2 * k2;
-      const bool kok = k < K;
-      const long long ko = kok ? lvl_off(Lk, k) : 0;
+      const long long ko = kof[2 * k2];
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
         const int r = tid / CPR + i * (NT / CPR);
         const long long ro = rowoff[r];
-        const bool ok = kok && ro >= 0;
+        const bool ok = ko >= 0 && ro >= 0;
         cp_async16(s + r * LD + 2 * k2, ok ? g + ro + ko : g, ok);
       }
     } else {
       constexpr int ITER = BR * BK / NT;
       const int kl = tid % BK;
-      const int k = k0 + kl;
-      const bool kok = k < K;
-      const long long ko = kok ? lvl_off(Lk, k) : 0;
+      const long long ko = kof[kl];
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
         const int r = tid / BK + i * (NT / BK);
         const long long ro = rowoff[r];
-        const bool ok = kok && ro >= 0;
+        const bool ok = ko >= 0 && ro >= 0;
         cp_async8(s + r * LD + kl, ok ? g + ro + ko : g, ok);
       }
     }
@@ -105,13 +107,11 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
       static_assert(NT % CPK == 0, "tile/thread mismatch");
       const int r2 = tid % CPK;
       const long long ro = rowoff[2 * r2];
-      const bool rok = ro >= 0;
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
         const int kl = tid / CPK + i * (NT / CPK);
-        const int k = k0 + kl;
-        const bool ok = rok && k < K;
-        const long long ko = ok ? lvl_off(Lk, k) : 0;
+        const long long ko = kof[kl];
+        const bool ok = ro >= 0 && ko >= 0;
         cp_async16(s + kl * LD + 2 * r2, ok ? g + ro + ko : g, ok);
       }
     } else {
@@ -119,13 +119,11 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
       static_assert(NT % BR == 0, "tile/thread mismatch");
       const int r = tid % BR;
       const long long ro = rowoff[r];
-      const bool rok = ro >= 0;
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
         const int kl = tid / BR + i * (NT / BR);
-        const int k = k0 + kl;
-        const bool ok = rok && k < K;
-        const long long ko = ok ? lvl_off(Lk, k) : 0;
+        const long long ko = kof[kl];
+        const bool ok = ro >= 0 && ko >= 0;
         cp_async8(s + kl * LD + r, ok ? g + ro + ko : g, ok);
       }
     }
@@ -147,29 +145,44 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   double* Bs = smem + STAGES * A_ELEMS;
   long long* rowA = reinterpret_cast<long long*>(Bs + STAGES * B_ELEMS);
   long long* rowB = rowA + BM;
+  long long* kofA = rowB + BN;                 // [STAGES][BK]
+  long long* kofB = kofA + STAGES * BK;        // [STAGES][BK]
 
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
-  const int bz = blockIdx.z;
+  const int S = d.splitk > 1 ? d.splitk : 1;
+  const int bz = blockIdx.z / S, sp = blockIdx.z - bz * S;
 
-  const double* gA = d.A + lvl_off(d.ab, bz);
-  const double* gB = d.B + lvl_off(d.bb, bz);
-  double* gC = d.C + lvl_off(d.cb, bz);
+  const double* gA = d.A + lvl_off_ni(d.ab, bz);
+  const double* gB = d.B + lvl_off_ni(d.bb, bz);
 
-  for (int r = tid; r < BM; r += NT) rowA[r] = (m0 + r < d.M) ? lvl_off(d.am, m0 + r) : -1;
-  for (int r = tid; r < BN; r += NT) rowB[r] = (n0 + r < d.N) ? lvl_off(d.bn, n0 + r) : -1;
+  // this CTA's K range (whole k-tiles)
+  const int K = d.K;
+  const int nkt_all = (K + BK - 1) / BK;
+  const int per = (nkt_all + S - 1) / S;
+  const int kt0 = sp * per;
+  const int nkt = max(0, min(per, nkt_all - kt0));
+  const int kbase = kt0 * BK;
+
+  for (int r = tid; r < BM; r += NT) rowA[r] = (m0 + r < d.M) ? lvl_off_ni(d.am, m0 + r) : -1;
+  for (int r = tid; r < BN; r += NT) rowB[r] = (n0 + r < d.N) ? lvl_off_ni(d.bn, n0 + r) : -1;
+  // k-offset tables of the first STAGES tiles
+  for (int q = tid; q < 2 * STAGES * BK; q += NT) {
+    const int which = q / (STAGES * BK), rem = q % (STAGES * BK);
+    const int k = kbase + rem;                                   // tile (rem / BK) sits in slot (rem / BK)
+    const long long o = (rem / BK < nkt && k < K) ? lvl_off_ni(which ? d.bk : d.ak, k) : -1;
+    (which ? kofB : kofA)[rem] = o;
+  }
   __syncthreads();
 
-  const int K = d.K;
-  const int nkt = (K + BK - 1) / BK;
   const bool avec = d.a_vec != 0, bvec = d.b_vec != 0;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nkt) {
-      load_tile<BM, NT, AKF>(As + s * A_ELEMS, gA, rowA, d.ak, s * BK, K, avec, tid);
-      load_tile<BN, NT, BKF>(Bs + s * B_ELEMS, gB, rowB, d.bk, s * BK, K, bvec, tid);
+      load_tile<BM, NT, AKF>(As + s * A_ELEMS, gA, rowA, kofA + s * BK, avec, tid);
+      load_tile<BN, NT, BKF>(Bs + s * B_ELEMS, gB, rowB, kofB + s * BK, bvec, tid);
     }
     cp_async_commit();
   }
@@ -192,10 +205,18 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
       const int nk = kt + STAGES - 1;
       if (nk < nkt) {
         const int s = nk % STAGES;
-        load_tile<BM, NT, AKF>(As + s * A_ELEMS, gA, rowA, d.ak, nk * BK, K, avec, tid);
-        load_tile<BN, NT, BKF>(Bs + s * B_ELEMS, gB, rowB, d.bk, nk * BK, K, bvec, tid);
+        load_tile<BM, NT, AKF>(As + s * A_ELEMS, gA, rowA, kofA + s * BK, avec, tid);
+        load_tile<BN, NT, BKF>(Bs + s * B_ELEMS, gB, rowB, kofB + s * BK, bvec, tid);
       }
       cp_async_commit();
+      // k-offsets of tile kt+STAGES go into the slot tile kt used (its loads were issued two iterations ago);
+      // they are read after the next iteration's barrier
+      const int fk = kt + STAGES;
+      if (tid < 2 * BK && fk < nkt) {
+        const int which = tid / BK, kl = tid % BK;
+        const int k = kbase + fk * BK + kl;
+        (which ? kofB : kofA)[(fk % STAGES) * BK + kl] = k < K ? lvl_off_ni(which ? d.bk : d.ak, k) : -1;
+      }
     }
     const double* as = As + (kt % STAGES) * A_ELEMS;
     const double* bs = Bs + (kt % STAGES) * B_ELEMS;
@@ -222,6 +243,25 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   cp_async_wait<0>();
 
   // epilogue: thread holds C[m = wm0+8i+g][n = wn0+8j+2t+{0,1}]
+  if (S > 1) {
+    // split-K: raw partial tile to the workspace [batch][split][N][M]; k_splitk_reduce applies alpha/beta
+    double* ws = d.ws + ((long long)blockIdx.z) * d.M * (long long)d.N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = m0 + wm0 + i * 8 + g;
+      if (m < d.M) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = n0 + wn0 + j * 8 + 2 * t + e;
+            if (n < d.N) ws[m + (long long)d.M * n] = acc[i][j][e];
+          }
+      }
+    }
+    return;
+  }
+  double* gC = d.C + lvl_off_ni(d.cb, bz);
   const double alpha = d.alpha, beta = d.beta;
   long long coff[TN][2];
   bool cok[TN][2];
@@ -231,13 +271,13 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
     for (int e = 0; e < 2; ++e) {
       const int n = n0 + wn0 + j * 8 + 2 * t + e;
       cok[j][e] = n < d.N;
-      coff[j][e] = cok[j][e] ? lvl_off(d.cn, n) : 0;
+      coff[j][e] = cok[j][e] ? lvl_off_ni(d.cn, n) : 0;
     }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + wm0 + i * 8 + g;
     if (m < d.M) {
-      const long long ro = lvl_off(d.cm, m);
+      const long long ro = lvl_off_ni(d.cm, m);
 #pragma unroll
       for (int j = 0; j < TN; ++j)
 #pragma unroll
@@ -252,23 +292,50 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   }
 }
 
+// C = alpha * sum_s ws[b][s] + beta * C   (fixed summation order: deterministic)
+__global__ void k_splitk_reduce(const __grid_constant__ GemmDesc d) {
+  const long long MN = (long long)d.M * d.N;
+  const long long total = MN * d.batch;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / MN);
+    const long long r = idx - (long long)b * MN;
+    const int m = (int)(r % d.M), n = (int)(r / d.M);
+    double v = 0.0;
+    for (int s = 0; s < d.splitk; ++s) v += d.ws[((long long)b * d.splitk + s) * MN + r];
+    double* pc = d.C + lvl_off(d.cb, b) + lvl_off(d.cm, m) + lvl_off(d.cn, n);
+    v *= d.alpha;
+    if (d.beta != 0.0) v += d.beta * *pc;
+    *pc = v;
+  }
+}
+
 template <int BM, int BN, int WM, int WN, bool AKF, bool BKF>
 void launch_cfg(tnad_ctx* c, const GemmDesc& d) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr int A_ELEMS = AKF ? BM * (BK + 4) : BK * (BM + 4);
   constexpr int B_ELEMS = BKF ? BN * (BK + 4) : BK * (BN + 4);
-  const size_t smem = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double) + (BM + BN) * sizeof(long long);
+  const size_t smem = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double) +
+                      (BM + BN + 2 * STAGES * BK) * sizeof(long long);
   static bool attr_set = false;
   auto kern = gemm_dmma_kernel<BM, BN, WM, WN, AKF, BKF>;
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.batch);
+  const int S = d.splitk > 1 ? d.splitk : 1;
+  dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.batch * S);
   KTimer kt(c, KF_GEMM);
   kern<<<grid, NT, smem, c->stream>>>(d);
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
+  if (S > 1) {
+    const long long total = (long long)d.M * d.N * d.batch;
+    int nb = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    k_splitk_reduce<<<nb < 1 ? 1 : nb, 256, 0, c->stream>>>(d);
+    c->launches++;
+    TNAD_CUDA(cudaGetLastError());
+  }
 }
 
 template <int BM, int BN, int WM, int WN>
@@ -284,14 +351,30 @@ void launch_layout(tnad_ctx* c, const GemmDesc& d) {
 
 }  // namespace
 
-void gemm_run(tnad_ctx* c, const GemmDesc& d) {
-  if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return;
-  TNAD_REQUIRE(d.batch <= 65535 && (d.N + 63) / 64 <= 65535, "gemm: grid too large");
-  const long long big_tiles = (long long)((d.M + 127) / 128) * ((d.N + 127) / 128) * d.batch;
-  if (big_tiles >= c->num_sms / 2 && d.M >= 96 && d.N >= 96)
-    launch_layout<128, 128, 64, 32>(c, d);
-  else
-    launch_layout<64, 64, 32, 32>(c, d);
+void gemm_run(tnad_ctx* c, const GemmDesc& d0) {
+  if (d0.M <= 0 || d0.N <= 0 || d0.batch <= 0) return;
+  GemmDesc d = d0;
+  const bool large = d.M >= 96 && d.N >= 96;
+  const int bm = large ? 128 : 64;
+  const long long tiles = (long long)((d.M + bm - 1) / bm) * ((d.N + bm - 1) / bm) * d.batch;
+  // split-K when the output tiles alone cannot fill the machine (small M x N, long K: the projector and
+  // svd_back products of the CTMRG step); partial tiles are summed in a fixed order by k_splitk_reduce
+  const int nkt = (d.K + BK - 1) / BK;
+  int S = 1;
+  if (tiles < c->num_sms && nkt >= 8) {
+    S = (int)std::min<long long>((2LL * c->num_sms + tiles - 1) / tiles, nkt / 4);
+    S = std::max(1, std::min(S, 64));
+  }
+  TNAD_REQUIRE((long long)d.batch * S <= 65535 && (d.N + 63) / 64 <= 65535, "gemm: grid too large");
+  Tens ws;
+  d.splitk = S;
+  d.ws = nullptr;
+  if (S > 1) {
+    ws = t_alloc(c, {(int64_t)d.M * d.N * d.batch * S});
+    d.ws = ws.p;
+  }
+  if (large) launch_layout<128, 128, 64, 32>(c, d);
+  else launch_layout<64, 64, 32, 32>(c, d);
 }
 
 }  // namespace tnad
