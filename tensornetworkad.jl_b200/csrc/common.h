@@ -230,10 +230,12 @@ struct SvdResult {
   std::vector<double> s_host;
   double null_thr = 0.0;   // singular values <= null_thr are numerically null (their U columns are a completion)
   int sweeps = 0;
+  int64_t rank_left = -1;   // >= 0: only the first rank_left columns of U are valid (null columns left zero)
 };
 // A: any rank-2 strided view (m x n). If sym_add_transpose, the matrix decomposed is A + A^T (m == n).
 // V0 (optional, n x n orthogonal): warm start for square inputs.
-SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false, const Tens* V0 = nullptr);
+SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false, const Tens* V0 = nullptr,
+                     bool complete_null = true);
 
 // Symmetric input (ctmrg.jl:135-136): two-sided block Jacobi eigensolver, M = Q L Q' -> U = Q, S = |L|, V = Q sign(L).
 SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose = false, const Tens* Q0 = nullptr);

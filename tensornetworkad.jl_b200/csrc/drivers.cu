@@ -13,12 +13,28 @@ namespace tnad {
 // svd_back
 // =====================================================================================================
 Tens svd_back_dev(tnad_ctx* c, const Tens& U, const Tens& S, const Tens& V, const Tens* dUk, const Tens* dS,
-                  const Tens* dVk, int64_t k, double eta) {
+                  const Tens* dVk, int64_t k, double eta, int64_t r_valid) {
   Span sp(c, 4);
   const int64_t m = U.dim[0], n = V.dim[0], kk = S.dim[0];
   TNAD_REQUIRE(U.dim[1] == kk && V.dim[1] == kk && k <= kk, "svd_back: shape mismatch");
+  // r_valid < kk: the columns r_valid.. of U (exactly-zero singular values) were not computed; their only
+  // contribution, sum_i U_i U_i' dU_j / S_j, is applied as the projector (I - U_r U_r') instead.
+  const bool proj = r_valid >= 0 && r_valid < kk && dUk != nullptr;
+  const int64_t ru = proj ? r_valid : kk;
+  Tens Ur = t_slice_last(U, 0, ru);
   Tens G1, G2;
-  if (dUk) G1 = contract_new(c, "mi,mj->ij", U, *dUk);   // (U' dU)[:, :k]
+  if (dUk) {
+    if (proj) {
+      G1 = t_alloc(c, {kk, k}, true);
+      if (ru > 0) {
+        Tens G1r = t_wrap(G1.p, {ru, k});
+        G1r.str[1] = kk;
+        contract(c, "mi,mj->ij", Ur, *dUk, G1r, 1.0, 0.0);
+      }
+    } else {
+      G1 = contract_new(c, "mi,mj->ij", U, *dUk);   // (U' dU)[:, :k]
+    }
+  }
   if (dVk) G2 = contract_new(c, "ni,nj->ij", V, *dVk);
   Tens Rrow = t_alloc(c, {k, kk});
   Tens Rcol = t_alloc(c, {kk, k});
@@ -28,7 +44,21 @@ Tens svd_back_dev(tnad_ctx* c, const Tens& U, const Tens& S, const Tens& V, cons
   // dA = U[:, :k] (Rrow V') + (U Rcol) V[:, :k]'
   Tens T1 = contract_new(c, "ij,nj->in", Rrow, V);
   Tens dA = contract_new(c, "mi,in->mn", Uk, T1);
-  Tens T2 = contract_new(c, "mi,ij->mj", U, Rcol);
+  Tens T2;
+  if (proj) {
+    Tens Rc = t_wrap(Rcol.p, {ru, k});
+    Rc.str[1] = kk;
+    T2 = t_clone(c, *dUk);                                    // (dU - U_r U_r'dU) Sinv  +  U_r Rcol_r
+    if (ru > 0) {
+      Tens G1r = t_wrap(G1.p, {ru, k});
+      G1r.str[1] = kk;
+      contract(c, "mi,ij->mj", Ur, G1r, T2, -1.0, 1.0);
+    }
+    colscale_sinv(c, T2.p, m, m, k, S.p, eta);
+    if (ru > 0) contract(c, "mi,ij->mj", Ur, Rc, T2, 1.0, 1.0);
+  } else {
+    T2 = contract_new(c, "mi,ij->mj", U, Rcol);
+  }
   contract(c, "mj,nj->mn", T2, Vk, dA, 1.0, 1.0);
   if (dUk && m != kk) {   // (dU - U U'dU) Sinv V'   (trg.jl:97-99)
     Tens P = t_clone(c, *dUk);
@@ -64,7 +94,7 @@ TrgSplit trg_split(tnad_ctx* c, const Tens& t4, int64_t dmax, double tol) {
   TrgSplit sp;
   {
     Span s(c, 1);
-    sp.svd = svd_jacobi(c, t4, false);
+    sp.svd = svd_jacobi(c, t4, false, nullptr, /*complete_null=*/false);
   }
   const int64_t m = t4.dim[0] * t4.dim[1], n = t4.dim[2] * t4.dim[3];
   sp.k = trg_rank_rule(sp.svd.s_host, dmax, tol);
@@ -147,7 +177,7 @@ static Tens trg_split_back(tnad_ctx* c, const TrgSplit& sp, const Tens& du /*(d1
   const int64_t m = sp.svd.U.dim[0], n = sp.svd.V.dim[0], k = sp.k;
   Tens dUk = t_alloc(c, {m, k}), dVk = t_alloc(c, {n, k}), dS = t_alloc(c, {k});
   trg_factor_back(c, m, n, k, sp.svd.U.p, m, sp.svd.V.p, n, sp.svd.S.p, du.p, dvt.p, dUk.p, dVk.p, dS.p);
-  return svd_back_dev(c, sp.svd.U, sp.svd.S, sp.svd.V, &dUk, &dS, &dVk, k, eta);
+  return svd_back_dev(c, sp.svd.U, sp.svd.S, sp.svd.V, &dUk, &dS, &dVk, k, eta, sp.svd.rank_left);
 }
 
 Tens trg_backward(tnad_ctx* c, TrgTape& tape, double dlnZ) {

@@ -21,6 +21,10 @@
 
 namespace tnad {
 
+void launch_gram_pivot_eig(tnad_ctx* c, const double* Hpart, int nsplit, int npairs, int p, int round, int nreal,
+                           const double* fro2, double tol_rel, double nullfac, int max_inner, int cross, double* Wbuf,
+                           int* skip, unsigned long long* offbits, cudaStream_t st);   // symeig.cu
+
 namespace {
 
 constexpr int JB = 32;        // block width
@@ -415,7 +419,8 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int depth, const Tens* V0) {
+static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int depth, const Tens* V0,
+                                 bool complete_null) {
   TNAD_REQUIRE(Ain0.rank == 2 || Ain0.rank == 4, "svd: need a matrix or a rank-4 view [(i0,i1),(j0,j1)]");
   Tens Ain = Ain0;
   if (Ain0.rank == 2) {   // promote to rank 4 with unit middle dims
@@ -496,10 +501,16 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   const double eps = 2.220446049250313e-16;
   const double tol = std::max(8.0, 2.0 * std::sqrt((double)m)) * eps;
   // numerically-null threshold on squared column norms: (4 eps)^2 max(m,n) |A|_F^2
-  const double nullfac = 16.0 * eps * eps * (double)std::max(m, n);
+  double nullfac = 16.0 * eps * eps * (double)std::max(m, n);
+  if (const char* nr = getenv("TNAD_NULL_REL")) {   // experiment: freeze columns below nr * |A|_F
+    const double v = atof(nr);
+    if (v > 0.0) nullfac = v * v;
+  }
   double* fro2 = c->scal + 18;
   reduce(c, RED_SUMSQ, G, nullptr, fro2);
   const bool debug = env_int("TNAD_JACOBI_DEBUG", 0) != 0;
+  const bool old_eig = env_int("TNAD_OLD_EIG", 0) != 0;
+  const bool cross_mode = env_int("TNAD_JACOBI_CROSS", 0) != 0;
   const int max_inner = env_int("TNAD_JACOBI_INNER", 1);
   const int max_sweeps = env_int("TNAD_JACOBI_SWEEPS", 60);
 
@@ -518,8 +529,12 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
       LAUNCH_CHECK(c);
       {
       KTimer kt(c, KF_EIG);
-      k_jacobi_eig<<<npairs, 512, smem_eig, c->stream>>>(Hpart.p, nsplit, tol, max_inner, fro2, nullfac, p, r, (int)n, Wbuf.p, skip,
-                                                        offbits);
+      if (old_eig)
+        k_jacobi_eig<<<npairs, 512, smem_eig, c->stream>>>(Hpart.p, nsplit, tol, max_inner, fro2, nullfac, p, r, (int)n, Wbuf.p,
+                                                          skip, offbits);
+      else   // register-resident pivot kernel (symeig.cu); cross-only schedule after the sweep's first round
+        launch_gram_pivot_eig(c, Hpart.p, nsplit, npairs, p, r, (int)n, fro2, tol, nullfac, max_inner, (cross_mode && r > 0) ? 1 : 0,
+                              Wbuf.p, skip, offbits, nullptr);
       }
       LAUNCH_CHECK(c);
       {
@@ -585,7 +600,10 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   TNAD_CUDA(cudaMemcpyAsync(S.p, dsval, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   sync(c);   // perm/sval/isnull host vectors must outlive the async uploads
 
-  if (!sym && !nullcols.empty()) {
+  if (!sym && !nullcols.empty() && !complete_null && !transposed) {
+    // the caller (TRG) handles the left null space through the projector I - U_r U_r' in svd_back
+    res.rank_left = n - (int64_t)nullcols.size();
+  } else if (!sym && !nullcols.empty()) {
     // Orthonormal completion of the left null space (needed because svd_back uses the full U):
     // project a random block out of span(U_range) twice, then orthonormalise it with the same
     // Jacobi kernels (left singular vectors of a full-column-rank block).
@@ -605,7 +623,7 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
         contract(c, "mr,rq->mq", Ur, Cm, Wr, -1.0, 1.0);
       }
     }
-    SvdResult wn = svd_jacobi_impl(c, Wr, false, depth + 1, nullptr);
+    SvdResult wn = svd_jacobi_impl(c, Wr, false, depth + 1, nullptr, true);
     TNAD_CUDA(cudaMemcpyAsync(U.p + r * m, wn.U.p, (size_t)(m * q) * sizeof(double), cudaMemcpyDeviceToDevice,
                               c->stream));
   }
@@ -637,8 +655,8 @@ void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int 
   LAUNCH_CHECK(c);
 }
 
-SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* V0) {
-  return svd_jacobi_impl(c, A, sym_add_transpose, 0, V0);
+SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* V0, bool complete_null) {
+  return svd_jacobi_impl(c, A, sym_add_transpose, 0, V0, complete_null);
 }
 
 }  // namespace tnad

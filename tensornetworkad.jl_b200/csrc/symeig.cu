@@ -83,11 +83,17 @@ __device__ __forceinline__ long long pair_index(int I, int J, int r) {   // r in
 constexpr int EW = 8;            // warps
 constexpr int ER = JP / EW;      // rows per warp
 
-__global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ M, long long ld, int p, int round,
-                                                     int nreal, const double* __restrict__ fro2, double tolfac,
-                                                     int max_inner, int cross, double* __restrict__ Wbuf,
-                                                     int* __restrict__ skip,
-                                                     unsigned long long* __restrict__ offmax_bits) {
+// GRAM == false: P is the pivot block of the symmetric matrix M (absolute threshold tolfac * |M|_F).
+// GRAM == true : P is the Gram matrix X'X of a column pair of the one-sided method (jacobi.cu), summed from
+//                `nsplit` partial products; thresholds are relative (cosines) and numerically-null columns
+//                (squared norm <= nullfac * |A|_F^2) are frozen.
+template <bool GRAM>
+__global__ void __launch_bounds__(EW * 32) k_pivot_eig(const double* __restrict__ M, long long ld, int p, int round,
+                                                       int nreal, const double* __restrict__ fro2, double tolfac,
+                                                       int max_inner, int cross, double* __restrict__ Wbuf,
+                                                       int* __restrict__ skip,
+                                                       unsigned long long* __restrict__ offmax_bits, int nsplit,
+                                                       double nullfac) {
   __shared__ double Ps[JP * HLD];
   __shared__ double part[2][EW][32][3];
   __shared__ double red[EW];
@@ -95,16 +101,33 @@ __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ 
   const int pair = blockIdx.x, tid = threadIdx.x, w = tid >> 5, k = tid & 31;
   int I, J;
   rr_pair(p, round, pair, I, J);
-  const double tol = tolfac * sqrt(*fro2);   // absolute threshold on off-diagonal entries
-  for (int idx = tid; idx < JP * JP; idx += EW * 32) {
-    const int r = idx % JP, c = idx / JP;
-    Ps[r * HLD + c] = M[pair_index(I, J, r) + pair_index(I, J, c) * ld];
+  const double tol = GRAM ? tolfac : tolfac * sqrt(*fro2);   // relative (cosine) / absolute threshold
+  const double thr2 = GRAM ? nullfac * (*fro2) : 0.0;
+  if (GRAM) {
+    const double* hp = M + (long long)pair * nsplit * (JP * JP);
+    for (int idx = tid; idx < JP * JP; idx += EW * 32) {
+      double h = 0.0;
+      for (int sidx = 0; sidx < nsplit; ++sidx) h += hp[(long long)sidx * (JP * JP) + idx];
+      Ps[(idx % JP) * HLD + idx / JP] = h;
+    }
+  } else {
+    for (int idx = tid; idx < JP * JP; idx += EW * 32) {
+      const int r = idx % JP, c = idx / JP;
+      Ps[r * HLD + c] = M[pair_index(I, J, r) + pair_index(I, J, c) * ld];
+    }
   }
   __syncthreads();
   double off = 0.0;
   for (int idx = tid; idx < JP * JP; idx += EW * 32) {
     const int r = idx % JP, c = idx / JP;
-    if (r < c) off = fmax(off, fabs(Ps[r * HLD + c]));
+    if (r < c) {
+      if (GRAM) {
+        const double hr = Ps[r * HLD + r], hc = Ps[c * HLD + c];
+        if (hr > thr2 && hc > thr2) off = fmax(off, fabs(Ps[r * HLD + c]) * rsqrt(hr * hc));
+      } else {
+        off = fmax(off, fabs(Ps[r * HLD + c]));
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
@@ -159,7 +182,7 @@ __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ 
         apq += part[buf][v][k][2];
       }
       buf ^= 1;
-      if (apq * apq > tol2) {
+      if (GRAM ? (app > thr2 && aqq > thr2 && apq * apq > tol2 * app * aqq) : (apq * apq > tol2)) {
         const double tau = aqq - app;
         const double ww = tau * tau + 4.0 * apq * apq;
         const double d = fabs(tau) + ww * rsqrt(ww);
@@ -233,8 +256,8 @@ __global__ void __launch_bounds__(EW * 32) k_sym_eig(const double* __restrict__ 
       lb += part[buf][v][k][1];
     }
     if (w == 0) {   // key: |lambda|; padding columns (exactly zero rows and columns of M) stay last
-      keys[k] = pair_index(I, J, ot) >= nreal ? -1.0 : fabs(lt);
-      keys[JB + k] = pair_index(I, J, ob) >= nreal ? -1.0 : fabs(lb);
+      keys[k] = pair_index(I, J, ot) >= nreal ? -1.0 : (GRAM ? fmax(lt, 0.0) : fabs(lt));
+      keys[JB + k] = pair_index(I, J, ob) >= nreal ? -1.0 : (GRAM ? fmax(lb, 0.0) : fabs(lb));
     }
     __syncthreads();
   }
@@ -429,6 +452,16 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+// Gram-matrix pivot problem of the one-sided method (jacobi.cu): same register-resident kernel.
+void launch_gram_pivot_eig(tnad_ctx* c, const double* Hpart, int nsplit, int npairs, int p, int round, int nreal,
+                           const double* fro2, double tol_rel, double nullfac, int max_inner, int cross, double* Wbuf,
+                           int* skip, unsigned long long* offbits, cudaStream_t st) {
+  k_pivot_eig<true><<<npairs, EW * 32, 0, st ? st : c->stream>>>(Hpart, 0, p, round, nreal, fro2, tol_rel, max_inner, cross,
+                                                                Wbuf, skip, offbits, nsplit, nullfac);
+  c->launches++;
+  TNAD_CUDA(cudaGetLastError());
+}
+
 }  // namespace tnad
 
 // Per-context cache: work buffers, look-ahead tables and the captured one-sweep CUDA graph, keyed by n.
@@ -582,8 +615,8 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
       for (int r = 0; r < nr; ++r) {
         {
           KTimer kt(c, KF_EIG);
-          k_sym_eig<<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, r, (int)n, fro2, tolfac, max_inner, (cross_mode && r > 0) ? 1 : 0, Wb[0], sk[0],
-                                               offbits);
+          k_pivot_eig<false><<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, r, (int)n, fro2, tolfac, max_inner,
+                                                         (cross_mode && r > 0) ? 1 : 0, Wb[0], sk[0], offbits, 0, 0.0);
         }
         {
           KTimer kt(c, KF_GRAM);
@@ -601,7 +634,8 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
     }
     {
       KTimer kt(c, KF_EIG);
-      k_sym_eig<<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, 0, (int)n, fro2, tolfac, max_inner, 0, Wb[0], sk[0], offbits);
+      k_pivot_eig<false><<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, 0, (int)n, fro2, tolfac, max_inner, 0, Wb[0], sk[0], offbits, 0,
+                                                     0.0);
     }
     ++nodes;
     for (int r = 0; r < nr; ++r) {
@@ -634,8 +668,8 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
       nodes += 3;
       if (r + 1 < nr) {
         KTimer kt(c, KF_EIG);
-        k_sym_eig<<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, r + 1, (int)n, fro2, tolfac, max_inner, cross_mode ? 1 : 0,
-                                             Wb[cur ^ 1], sk[cur ^ 1], offbits);
+        k_pivot_eig<false><<<npairs, EW * 32, 0, S1>>>(Mw.p, ld, p, r + 1, (int)n, fro2, tolfac, max_inner,
+                                                       cross_mode ? 1 : 0, Wb[cur ^ 1], sk[cur ^ 1], offbits, 0, 0.0);
         ++nodes;
       }
     }
