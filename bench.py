@@ -143,6 +143,11 @@ def cpu_reference_sample(sample_maxit):
     on a bounded sample of the workload: same tensor, same chi, `maxit = sample_maxit`."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import tnad_oracle as O
+    try:    # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core it can use
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     h, A = heisenberg_h(), ipeps_tensor(0)
     info = {}
     t0 = time.perf_counter()
