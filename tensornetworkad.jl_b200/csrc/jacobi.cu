@@ -5,9 +5,9 @@
 // load) and V as the identity.  Columns are grouped in blocks of 32; a sweep visits every block pair
 // once in round-robin order, all N/64 pairs of a round in parallel:
 //   1. k_jacobi_gram   H = X^T X for X = [G_I G_J] (64 columns), rows split over CTAs, DMMA.
-//   2. k_jacobi_eig    sums the partial Grams and diagonalises the 64x64 H with a cyclic two-sided
-//                      Jacobi in shared memory (32 disjoint rotations per step) -> W; a pair whose
-//                      largest cosine is already below tol is skipped.
+//   2. k_pivot_eig<GRAM> (symeig.cu) sums the partial Grams and diagonalises the 64x64 H with the
+//                      register-resident implicit Jacobi kernel (32 disjoint rotations per step) -> W;
+//                      a pair whose largest cosine is already below tol is skipped.
 //   3. k_jacobi_update [G_I G_J] <- [G_I G_J] W and [V_I V_J] <- [V_I V_J] W, in place, DMMA.
 // At convergence G = A V has orthogonal columns: S = column norms, U = G / S.  Exactly-null columns
 // get an orthonormal completion (V's own column for the symmetric case, projected random vectors
@@ -126,144 +126,6 @@ __global__ void __launch_bounds__(256) k_jacobi_gram(const double* __restrict__ 
         const int m = 16 * wy + 8 * i + g, n = 32 * wx + 8 * j + 2 * t + e;
         out[m + JP * n] = acc[i][j][e];
       }
-}
-
-// ---- 2. 64x64 symmetric eigenproblem in shared memory -------------------------------------------
-__global__ void __launch_bounds__(512) k_jacobi_eig(const double* __restrict__ Hpart, int nsplit, double tol,
-                                                    int max_inner, const double* __restrict__ fro2, double nullfac,
-                                                    int p, int round, int nreal, double* __restrict__ Wbuf, int* __restrict__ skip,
-                                                    unsigned long long* __restrict__ offmax_bits) {
-  extern __shared__ __align__(16) double esm[];
-  double* H = esm;
-  double* W = H + JP * HLD;
-  double* red = W + JP * HLD;
-  double* dsort = red + 16;
-  int* perm = reinterpret_cast<int*>(dsort + JP);
-  const int pair = blockIdx.x, tid = threadIdx.x;
-  // columns whose squared norm is below thr2 = nullfac * |A|_F^2 are numerically null: they lie in
-  // the span of the other columns up to rounding, so their cosines never converge; freeze them.
-  const double thr2 = nullfac * (*fro2);
-  const double* hp = Hpart + (long long)pair * nsplit * (JP * JP);
-  for (int idx = tid; idx < JP * JP; idx += 512) {
-    double h = 0.0;
-    for (int s = 0; s < nsplit; ++s) h += hp[(long long)s * (JP * JP) + idx];
-    const int r = idx % JP, c = idx / JP;
-    H[r * HLD + c] = h;
-    W[r * HLD + c] = (r == c) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  // largest cosine between distinct non-null columns
-  double off = 0.0;
-  for (int idx = tid; idx < JP * JP; idx += 512) {
-    const int r = idx % JP, c = idx / JP;
-    if (r < c) {
-      const double hr = H[r * HLD + r], hc = H[c * HLD + c];
-      if (hr > thr2 && hc > thr2) off = fmax(off, fabs(H[r * HLD + c]) / sqrt(hr * hc));
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
-  if ((tid & 31) == 0) red[tid >> 5] = off;
-  __syncthreads();
-  if (tid == 0) {
-    double m = 0.0;
-    for (int i = 0; i < 16; ++i) m = fmax(m, red[i]);
-    red[0] = m;
-    atomicMax(offmax_bits, (unsigned long long)__double_as_longlong(m));
-    skip[pair] = (m <= tol) ? 1 : 0;
-  }
-  __syncthreads();
-  if (red[0] <= tol) return;
-
-  // Cyclic two-sided Jacobi, 32 disjoint rotations per step.  A half-warp owns one rotation: its 16
-  // lanes each compute the (identical) rotation parameters and apply them to 4 rows / columns.
-  const int kp = tid >> 4, l16 = tid & 15;
-  const double tol2 = tol * tol;
-  for (int sw = 0; sw < max_inner; ++sw) {
-    int rotated = 0;
-    for (int step = 0; step < JP - 1; ++step) {
-      int p_, q_;
-      rr_pair(JP, step, kp, p_, q_);
-      const double app = H[p_ * HLD + p_], aqq = H[q_ * HLD + q_], apq = H[p_ * HLD + q_];
-      __syncwarp();   // all lanes of the pair have read the pivot entries before anyone rotates them
-      const bool rot = app > thr2 && aqq > thr2 && apq * apq > tol2 * app * aqq;
-      double c = 1.0, s = 0.0;
-      if (rot) {
-        // t = sign(tau) 2 apq / (|tau| + sqrt(tau^2 + 4 apq^2)), tau = aqq - app; c = 1/sqrt(1+t^2); s = c t
-        const double tau = aqq - app;
-        const double w = tau * tau + 4.0 * apq * apq;
-        const double d = fabs(tau) + w * rsqrt(w);
-        const double rd = rsqrt(d);
-        const double tt = copysign(2.0 * apq * rd * rd, tau * apq);
-        c = rsqrt(1.0 + tt * tt);
-        s = c * tt;
-        rotated = 1;
-#pragma unroll
-        for (int r = 0; r < JP / 16; ++r) {
-          const int i = l16 + 16 * r;
-          const double hp = H[i * HLD + p_], hq = H[i * HLD + q_];
-          H[i * HLD + p_] = c * hp - s * hq;
-          H[i * HLD + q_] = s * hp + c * hq;
-          const double wp = W[i * HLD + p_], wq = W[i * HLD + q_];
-          W[i * HLD + p_] = c * wp - s * wq;
-          W[i * HLD + q_] = s * wp + c * wq;
-        }
-      }
-      __syncthreads();
-      if (rot) {
-#pragma unroll
-        for (int r = 0; r < JP / 16; ++r) {
-          const int j = l16 + 16 * r;
-          const double hp = H[p_ * HLD + j], hq = H[q_ * HLD + j];
-          H[p_ * HLD + j] = c * hp - s * hq;
-          H[q_ * HLD + j] = s * hp + c * hq;
-        }
-      }
-      __syncthreads();
-    }
-    if (!__syncthreads_or(rotated)) break;
-  }
-  if (tid < JP) {
-    // sort key: squared column norm; padding columns (global index >= nreal, exactly zero, V = e_j)
-    // must stay behind every real column, including real ones whose rounded norm came out <= 0.
-    int I, J;
-    rr_pair(p, round, pair, I, J);
-    const int gcol = tid < JB ? I * JB + tid : J * JB + tid - JB;
-    dsort[tid] = gcol >= nreal ? -1.0 : fmax(H[tid * HLD + tid], 0.0);
-  }
-  __syncthreads();
-  // Newton-Schulz polish  W <- W (1.5 I - 0.5 W'W): the product of ~100 plane rotations per column
-  // drifts from orthogonality by a few 1e-15, which would otherwise accumulate in V over a sweep.
-  for (int idx = tid; idx < JP * JP; idx += 512) {
-    const int i = idx % JP, j = idx / JP;
-    double t = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < JP; ++k) t += W[k * HLD + i] * W[k * HLD + j];
-    H[i * HLD + j] = (i == j ? 1.5 : 0.0) - 0.5 * t;
-  }
-  // de Rijk-style ordering: the rotated columns leave the pair sorted by decreasing norm (the
-  // diagonal of the diagonalised Gram matrix), so large columns migrate to low block indices and
-  // numerically-null ones collect in the last blocks, whose pairs are then skipped outright.
-  // The diagonal was saved to dsort before H is overwritten above.
-  __syncthreads();
-  if (tid < JP) {
-    const double dj = dsort[tid];
-    int rank = 0;
-    for (int i = 0; i < JP; ++i) {
-      const double di = dsort[i];
-      rank += (di > dj || (di == dj && i < tid)) ? 1 : 0;
-    }
-    perm[tid] = rank;
-  }
-  __syncthreads();
-  double* wout = Wbuf + (long long)pair * (JP * JP);
-  for (int idx = tid; idx < JP * JP; idx += 512) {
-    const int k = idx % JP, n = idx / JP;
-    double t = 0.0;
-#pragma unroll 8
-    for (int l = 0; l < JP; ++l) t += W[k * HLD + l] * H[l * HLD + n];
-    wout[k + JP * perm[n]] = t;
-  }
 }
 
 // ---- 3. rotate the column pair of G and V -------------------------------------------------------
@@ -446,9 +308,7 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   static bool attr_set = false;
   const size_t smem_gram = (size_t)JP * XLD * sizeof(double);
   const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
-  const size_t smem_eig = (size_t)(2 * JP * HLD + 16 + JP + JP) * sizeof(double);
   if (!attr_set) {
-    TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eig));
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gram));
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
     attr_set = true;
@@ -509,7 +369,6 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   double* fro2 = c->scal + 18;
   reduce(c, RED_SUMSQ, G, nullptr, fro2);
   const bool debug = env_int("TNAD_JACOBI_DEBUG", 0) != 0;
-  const bool old_eig = env_int("TNAD_OLD_EIG", 0) != 0;
   const bool cross_mode = env_int("TNAD_JACOBI_CROSS", 0) != 0;
   const int max_inner = env_int("TNAD_JACOBI_INNER", 1);
   const int max_sweeps = env_int("TNAD_JACOBI_SWEEPS", 60);
@@ -529,10 +388,7 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
       LAUNCH_CHECK(c);
       {
       KTimer kt(c, KF_EIG);
-      if (old_eig)
-        k_jacobi_eig<<<npairs, 512, smem_eig, c->stream>>>(Hpart.p, nsplit, tol, max_inner, fro2, nullfac, p, r, (int)n, Wbuf.p,
-                                                          skip, offbits);
-      else   // register-resident pivot kernel (symeig.cu); cross-only schedule after the sweep's first round
+      // register-resident pivot kernel (symeig.cu, Gram mode)
         launch_gram_pivot_eig(c, Hpart.p, nsplit, npairs, p, r, (int)n, fro2, tol, nullfac, max_inner, (cross_mode && r > 0) ? 1 : 0,
                               Wbuf.p, skip, offbits, nullptr);
       }

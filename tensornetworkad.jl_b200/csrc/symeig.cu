@@ -641,10 +641,7 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
     for (int r = 0; r < nr; ++r) {
       const int cur = r & 1;
       TNAD_CUDA(cudaEventRecord(c->ev_eig, S1));
-      if (r > 0) {
-        TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_rest, 0));   // M fully updated by round r-1
-        TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_v, 0));      // W[cur^1] no longer read by the Q update of round r-1
-      }
+      if (r > 0) TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_rest, 0));   // M fully updated by round r-1
       {
         KTimer kt(c, KF_GRAM);
         k_sym_update_m<<<sc->pcount[r], 256, smem_upd, S1>>>(Mw.p, ld, p, r, Wb[cur], sk[cur], 1,
@@ -658,6 +655,9 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
                                                                    prio_d + (size_t)r * npairs * npairs, npairs, wc_m);
       }
       TNAD_CUDA(cudaEventRecord(c->ev_rest, S2));
+      // the next pivot kernel overwrites W[cur^1], which the Q update of round r-1 (stream 3) may still read:
+      // wait for it here, before ev_v is re-recorded for round r
+      if (r > 0) TNAD_CUDA(cudaStreamWaitEvent(S1, c->ev_v, 0));
       TNAD_CUDA(cudaStreamWaitEvent(S3, c->ev_eig, 0));
       {
         KTimer kt(c, KF_UPDATE, S3);
