@@ -87,6 +87,58 @@ def test_svd_large_symmetric(ctx):
     _check_svd(ctx, A + A.T, tol_rec=2e-13)
 
 
+def _check_svd_sym(ctx, A, tol_rec=5e-13):
+    U, S, V = ctx.svd_sym(A)
+    n = A.shape[0]
+    Sref = np.linalg.svd(A, compute_uv=False)
+    scale = max(Sref[0], 1e-300)
+    assert np.linalg.norm((U * S) @ V.T - A) <= tol_rec * max(np.linalg.norm(A), 1e-300)
+    assert np.abs(U.T @ U - np.eye(n)).max() < 1e-12 and np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+    assert np.abs(S - Sref).max() / scale < 1e-12 and np.all(np.diff(S) <= 0)
+    # V = U sign(lambda): columns of U are eigenvectors
+    lam = np.einsum("ij,ij->j", U, A @ U)
+    assert np.abs(np.abs(lam) - S).max() / scale < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 31, 64, 65, 100, 200, 512])
+def test_svd_sym_random(ctx, n):
+    A = np.random.default_rng(n).standard_normal((n, n))
+    _check_svd_sym(ctx, A + A.T)
+
+
+def test_svd_sym_structured(ctx):
+    rng = np.random.default_rng(8)
+    Q, _ = np.linalg.qr(rng.standard_normal((96, 96)))
+    lam = np.concatenate([np.linspace(1, 2, 40), -np.linspace(1.01, 2.01, 40), np.zeros(16)])   # indefinite + null space
+    _check_svd_sym(ctx, (Q * lam) @ Q.T)
+    lam = np.concatenate([np.logspace(0, -14, 80), np.zeros(16)]) * rng.choice([-1.0, 1.0], 96)  # graded spectrum
+    _check_svd_sym(ctx, (Q * lam) @ Q.T)
+    _check_svd_sym(ctx, np.diag(np.arange(1.0, 41.0)))
+    _check_svd_sym(ctx, np.ones((40, 40)))
+    B = rng.standard_normal((300, 12))
+    _check_svd_sym(ctx, B @ B.T)                                                                  # rank 12 of 300
+    U, S, V = ctx.svd_sym(np.zeros((10, 10)))
+    assert np.all(S == 0) and np.abs(U.T @ U - np.eye(10)).max() < 1e-14
+
+
+def test_svd_sym_matches_general_svd_on_ctmrg_matrix(ctx):
+    # the matrix ctmrgstep decomposes: cp + cp' for a random environment (ctmrg.jl:134-136)
+    rng = np.random.default_rng(12)
+    D, chi = 3, 14
+    bulk = rng.standard_normal((D, D, D, D)); bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
+    c, e = O.init_random(bulk, chi, rng)
+    X2 = np.einsum("ibd,dcl->ibcl", np.einsum("iba,ad->ibd", e, c), e)
+    cp = np.einsum("ibcl,jkcb->ijlk", X2, bulk).reshape(chi * D, chi * D, order="F")
+    M = cp + cp.T
+    U, S, V = ctx.svd_sym(M)
+    U2, S2, V2 = ctx.svd(M)
+    assert np.abs(S - S2).max() / S[0] < 1e-12
+    # leading subspace (what the projector z uses) agrees between the two solvers
+    P1, P2 = U[:, :chi] @ U[:, :chi].T, U2[:, :chi] @ U2[:, :chi].T
+    if S[chi - 1] - S[chi] > 1e-8 * S[0]:
+        assert np.abs(P1 - P2).max() < 1e-9
+
+
 def test_trg_svd_unit(ctx):
     # test/trg.jl:6-10
     rng = np.random.default_rng(0)
