@@ -317,11 +317,12 @@ void launch_cfg(tnad_ctx* c, const GemmDesc& d) {
   constexpr int B_ELEMS = BKF ? BN * (BK + 4) : BK * (BN + 4);
   const size_t smem = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double) +
                       (BM + BN + 2 * STAGES * BK) * sizeof(long long);
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
+  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
   auto kern = gemm_dmma_kernel<BM, BN, WM, WN, AKF, BKF>;
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_devs |= 1ULL << (c->device & 63);
   }
   const int S = d.splitk > 1 ? d.splitk : 1;
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.batch * S);

@@ -305,13 +305,14 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   const int npairs = p / 2;
   const int mchunks = (int)(mpad / RC), vchunks = (int)(ldv / RC);
 
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
+  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
   const size_t smem_gram = (size_t)JP * XLD * sizeof(double);
   const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gram));
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    attr_set = true;
+    attr_devs |= 1ULL << (c->device & 63);
   }
 
   Tens G = t_alloc(c, {mpad, N}, true);
@@ -500,11 +501,12 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
 // X[:, (I,J)] <- X[:, (I,J)] * W_pair for every pair of the round (X has ld rows in nchunks 128-row chunks)
 void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int p, int round, const double* Wbuf,
                            const int* skip, cudaStream_t st) {
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
+  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
   const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    attr_set = true;
+    attr_devs |= 1ULL << (c->device & 63);
   }
   k_jacobi_update<<<dim3(p / 2, nchunks), 256, smem_upd, st ? st : c->stream>>>(X, ld, nchunks, nullptr, 0, p, round, Wbuf, skip,
       c->ktiming ? reinterpret_cast<unsigned long long*>(c->scal + 21) : nullptr);

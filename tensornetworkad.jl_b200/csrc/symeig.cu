@@ -302,8 +302,7 @@ __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, lo
   if (work_counter && threadIdx.x == 0) atomicAdd(work_counter, 1ULL);   // executed blocks (roofline accounting)
   extern __shared__ __align__(16) double sm[];
   double* Xs = sm;                 // B, then T = Wa' B, then B' = T Wb; stored [col * BLD + row]
-  double* Was = Xs + JP * BLD;     // W_a column-major: Was[i * BLD + k] = W_a[k][i]
-  double* Wbs = Was + JP * BLD;
+  double* Ws = Xs + JP * BLD;      // W_a, then W_b (two buffers = 70 KB: three CTAs per SM); Ws[i * BLD + k] = W[k][i]
   const int tid = threadIdx.x;
   int Ia, Ja, Ib, Jb;
   rr_pair(p, round, a, Ia, Ja);
@@ -315,20 +314,16 @@ __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, lo
     const int col = q / (JP / 2), r2 = q % (JP / 2);
     const int r = 2 * r2;
     cp_async16(Xs + col * BLD + r, M + pair_index(Ia, Ja, r) + pair_index(Ib, Jb, col) * ld);
-    cp_async16(Was + col * BLD + r, Wbuf + (long long)a * (JP * JP) + col * JP + r);
-    cp_async16(Wbs + col * BLD + r, Wbuf + (long long)b * (JP * JP) + col * JP + r);
+    if (!ska) cp_async16(Ws + col * BLD + r, Wbuf + (long long)a * (JP * JP) + col * JP + r);
   }
+  if (ska)   // an untouched pair carries the identity (its Wbuf slot is stale)
+    for (int idx = tid; idx < JP * JP; idx += 256) Ws[(idx / JP) * BLD + idx % JP] = (idx / JP == idx % JP) ? 1.0 : 0.0;
   cp_async_wait_all();
   __syncthreads();
-  if (ska || skb) {   // an untouched pair carries the identity (its Wbuf slot is stale)
-    double* Wi = ska ? Was : Wbs;
-    for (int idx = tid; idx < JP * JP; idx += 256) Wi[(idx / JP) * BLD + idx % JP] = (idx / JP == idx % JP) ? 1.0 : 0.0;
-    __syncthreads();
-  }
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wy = warp & 3, wx = warp >> 2;   // rows 16*wy, cols 32*wx
   double acc[2][4][2];
-  // T = Wa' * B :  A[m=i][k] = W_a[k][i] = Was[i*BLD + k],  B[k][n=c] = Xs[c*BLD + k]
+  // T = Wa' * B :  A[m=i][k] = W_a[k][i] = Ws[i*BLD + k],  B[k][n=c] = Xs[c*BLD + k]
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -338,7 +333,7 @@ __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, lo
     const int k = kk * 4 + t;
     double af[2], bf[4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) af[i] = Was[(16 * wy + 8 * i + g) * BLD + k];
+    for (int i = 0; i < 2; ++i) af[i] = Ws[(16 * wy + 8 * i + g) * BLD + k];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bf[j] = Xs[(32 * wx + 8 * j + g) * BLD + k];
 #pragma unroll
@@ -346,15 +341,26 @@ __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, lo
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
   }
-  __syncthreads();   // everyone is done reading B
+  __syncthreads();   // everyone is done reading B and W_a
+  if (!skb) {
+#pragma unroll
+    for (int it = 0; it < (JP * JP / 2) / 256; ++it) {
+      const int q = tid + it * 256;
+      const int col = q / (JP / 2), r = 2 * (q % (JP / 2));
+      cp_async16(Ws + col * BLD + r, Wbuf + (long long)b * (JP * JP) + col * JP + r);
+    }
+  } else {
+    for (int idx = tid; idx < JP * JP; idx += 256) Ws[(idx / JP) * BLD + idx % JP] = (idx / JP == idx % JP) ? 1.0 : 0.0;
+  }
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) Xs[(32 * wx + 8 * j + 2 * t + e) * BLD + 16 * wy + 8 * i + g] = acc[i][j][e];
+  cp_async_wait_all();
   __syncthreads();
-  // B' = T * Wb :  A[m=i][k=c] = T[i][c] = Xs[c*BLD + i],  B[k=c][n=j] = W_b[c][j] = Wbs[j*BLD + c]
+  // B' = T * Wb :  A[m=i][k=c] = T[i][c] = Xs[c*BLD + i],  B[k=c][n=j] = W_b[c][j] = Ws[j*BLD + c]
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(256) k_sym_update_m(double* __restrict__ M, lo
 #pragma unroll
     for (int i = 0; i < 2; ++i) af[i] = Xs[k * BLD + 16 * wy + 8 * i + g];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bf[j] = Wbs[(32 * wx + 8 * j + g) * BLD + k];
+    for (int j = 0; j < 4; ++j) bf[j] = Ws[(32 * wx + 8 * j + g) * BLD + k];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -492,11 +498,12 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
   const int p = (int)(N / JB), npairs = p / 2, nr = p - 1;
   const int chunks = (int)((N + 127) / 128);
   const int64_t ld = (int64_t)chunks * 128;   // rows padded to the 128-row chunks of the panel kernel
-  const size_t smem_upd = (size_t)(3 * JP * BLD) * sizeof(double);
-  static bool attr_set = false;
+  const size_t smem_upd = (size_t)(2 * JP * BLD) * sizeof(double);
+  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
+  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_sym_update_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    attr_set = true;
+    attr_devs |= 1ULL << (c->device & 63);
   }
   const double eps = 2.220446049250313e-16;
   const double tolfac = 16.0 * eps;   // |m_pq| <= 16 eps |M|_F  (LAPACK-class absolute accuracy)
