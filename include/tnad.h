@@ -140,6 +140,15 @@ TNAD_API int tnad_energy(tnad_ctx* ctx, const double* h, const double* A, int d,
 TNAD_API int tnad_magnetisation_readout(tnad_ctx* ctx, const double* a, const double* m, int D,
                                const double* corner, const double* edge, int chi, double* mag);
 
+/* ---- pieces used by the chi-sharded multi-GPU step (tensornetworkad.jl_b200/sharded.py) -------- */
+/* svd(A + A') for a square A (ctmrg.jl:133-135: `cpmat += adjoint(cpmat); svd(cpmat)`), same solver as tnad_svd_sym */
+TNAD_API int tnad_svd_symmetrized(tnad_ctx* ctx, const double* A, int n, double* U, double* S, double* V, int* sweeps_out);
+/* permutedims(in, perm) (0-based perm, Julia semantics: out dim i = in dim perm[i]) */
+TNAD_API int tnad_permute(tnad_ctx* ctx, const double* in, const int64_t* dims, int rank, const int* perm, double* out);
+/* tail of ctmrgstep (ctmrg.jl:145-150): corner += corner', edge += permutedims(edge,(3,2,1)), each / its norm */
+TNAD_API int tnad_ctmrg_finish(tnad_ctx* ctx, const double* c1, const double* e1, int D, int chi,
+                               double* corner_out, double* edge_out);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* pinned host memory for end-to-end runs */
 TNAD_API int tnad_host_alloc(tnad_ctx* ctx, int64_t ndoubles, double** hptr);

@@ -61,6 +61,9 @@ SIGNATURES = {
     "tnad_magnetisation_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, c_double_p]),
     "tnad_last_timing": (C.c_int, [C.c_void_p, c_double_p]),
+    "tnad_svd_symmetrized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
+    "tnad_permute": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, c_int_p, C.c_void_p]),
+    "tnad_ctmrg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "tnad_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tnad_timer_start": (C.c_int, [C.c_void_p]),
@@ -368,6 +371,28 @@ class Context:
                                         _p(g), C.byref(steps)))
         self.last_steps = steps.value
         return (e.value, g) if grad else e.value
+
+    # ---- raw device-pointer calls (pointer mode DEVICE) used by sharded.py ---------------------------------
+    def dev_contract(self, spec, pa, dims_a, pb, dims_b, pc, alpha=1.0, beta=0.0):
+        da = (C.c_int64 * len(dims_a))(*dims_a)
+        db = (C.c_int64 * len(dims_b))(*dims_b)
+        self.check(self.lib.tnad_contract(self.h, spec.encode(), C.c_void_p(pa), da, len(dims_a), C.c_void_p(pb), db,
+                                          len(dims_b), float(alpha), float(beta), C.c_void_p(pc)))
+
+    def dev_permute(self, pin, dims, perm, pout):
+        dd = (C.c_int64 * len(dims))(*dims)
+        pp = (C.c_int * len(perm))(*perm)
+        self.check(self.lib.tnad_permute(self.h, C.c_void_p(pin), dd, len(dims), pp, C.c_void_p(pout)))
+
+    def dev_svd_symmetrized(self, pa, n, pu, ps, pv):
+        sw = C.c_int(0)
+        self.check(self.lib.tnad_svd_symmetrized(self.h, C.c_void_p(pa), int(n), C.c_void_p(pu), C.c_void_p(ps), C.c_void_p(pv),
+                                         C.byref(sw)))
+        return sw.value
+
+    def dev_ctmrg_finish(self, pc1, pe1, D, chi, pco, peo):
+        self.check(self.lib.tnad_ctmrg_finish(self.h, C.c_void_p(pc1), C.c_void_p(pe1), int(D), int(chi),
+                                              C.c_void_p(pco), C.c_void_p(peo)))
 
     def energy_device(self, h_dptr: int, A_dptr: int, d: int, s: int, chi: int, tol: float, maxit: int,
                       grad_dptr: int = 0):

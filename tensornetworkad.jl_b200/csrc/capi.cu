@@ -223,6 +223,18 @@ int tnad_svd_sym(tnad_ctx* c, const double* A, int n, double* U, double* S, doub
   TNAD_API_END(c)
 }
 
+int tnad_svd_symmetrized(tnad_ctx* c, const double* A, int n, double* U, double* S, double* V, int* sweeps_out) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(n >= 1, "tnad_svd_symmetrized: empty matrix");
+  Tens tA = t_in(c, A, {n, n});
+  SvdResult r = svd_symmetric(c, tA, true);
+  t_out(c, r.U, U);
+  t_out(c, r.S, S);
+  t_out(c, r.V, V);
+  if (sweeps_out) *sweeps_out = r.sweeps;
+  TNAD_API_END(c)
+}
+
 int tnad_trg_svd(tnad_ctx* c, const double* t, int d1, int d2, int d3, int d4, int dmax, double tol, double* u,
                  double* v, int* k_out) {
   TNAD_API_BEGIN(c)
@@ -373,6 +385,44 @@ int tnad_ctmrg_backward(tnad_ctx* c, tnad_tape* tape, const double* dcorner, con
   if (dcorner0) t_out(c, cb0, dcorner0);
   if (dedge0) t_out(c, eb0, dedge0);
   timing_end(c);
+  TNAD_API_END(c)
+}
+
+int tnad_permute(tnad_ctx* c, const double* in, const int64_t* dims, int rank, const int* perm, double* out) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(in && dims && perm && out && rank >= 1 && rank <= MAXR, "tnad_permute: bad arguments");
+  std::vector<int64_t> din(dims, dims + rank), dout((size_t)rank);
+  Tens tin = t_in(c, in, din);
+  Tens view = tin;
+  for (int i = 0; i < rank; ++i) {
+    TNAD_REQUIRE(perm[i] >= 0 && perm[i] < rank, "tnad_permute: bad permutation");
+    view.dim[i] = tin.dim[perm[i]];
+    view.str[i] = tin.str[perm[i]];
+    dout[(size_t)i] = tin.dim[perm[i]];
+  }
+  Tens tout = (c->pointer_mode == TNAD_POINTER_DEVICE) ? t_wrap(out, dout) : t_alloc_v(c, dout);
+  tcopy(c, view, tout, 1.0, 0.0);
+  if (c->pointer_mode == TNAD_POINTER_DEVICE) sync(c);
+  else t_out(c, tout, out);
+  TNAD_API_END(c)
+}
+
+int tnad_ctmrg_finish(tnad_ctx* c, const double* c1p, const double* e1p, int D, int chi, double* corner_out,
+                      double* edge_out) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && chi >= 1, "tnad_ctmrg_finish: bad arguments");
+  Tens c1 = t_in(c, c1p, {chi, chi}), e1 = t_in(c, e1p, {chi, D, chi});
+  Tens c2 = t_clone(c, c1), e2 = t_clone(c, e1);
+  tcopy(c, t_perm(c1, {1, 0}), c2, 1.0, 1.0);
+  tcopy(c, t_perm(e1, {2, 1, 0}), e2, 1.0, 1.0);
+  Tens ss = t_alloc(c, {2});
+  reduce(c, RED_SUMSQ, c2, nullptr, ss.p);
+  reduce(c, RED_SUMSQ, e2, nullptr, ss.p + 1);
+  Tens co = t_alloc(c, {chi, chi}), eo = t_alloc(c, {chi, D, chi});
+  scale_dev(c, c2, co, ss.p, SC_INVSQRT);
+  scale_dev(c, e2, eo, ss.p + 1, SC_INVSQRT);
+  t_out(c, co, corner_out);
+  t_out(c, eo, edge_out);
   TNAD_API_END(c)
 }
 

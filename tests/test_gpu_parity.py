@@ -416,3 +416,49 @@ def test_headline_shape_runs_and_is_consistent(ctx):
     assert abs(np.sum(g1 * A)) < 1e-9 * np.linalg.norm(g1)
     for p in [(0, 3, 2, 1, 4), (2, 1, 0, 3, 4), (1, 0, 3, 2, 4), (3, 2, 1, 0, 4)]:
         assert rel(np.transpose(g1, p), g1) < 1e-9        # gradient inherits the index-permutation symmetry
+
+
+# ---- chi-sharded step (tensornetworkad.jl_b200/sharded.py): world 1 here, world 2.. via bench_sharded.py -------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,chi", [(4, 8), (9, 12), (4, 32)])
+def test_sharded_step_single_rank_vs_oracle(ctx, D, chi):
+    from tnad_b200.sharded import ShardedCTMRG
+    rng = np.random.default_rng(D * 100 + chi)
+    bulk = rng.standard_normal((D, D, D, D))
+    bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
+    c, e = O.init_random(bulk, chi, rng)
+    cr, er, vr = O.ctmrgstep(bulk, c, e)
+    sh = ShardedCTMRG(ctx, chi, D)
+    sh.load(bulk, c, e)
+    sh.step()
+    cg, eg, vg = sh.result()
+    assert np.abs(vg - vr).max() < 1e-12
+    assert np.abs(np.abs(cg) - np.abs(cr)).max() < 1e-10 and np.abs(np.abs(eg) - np.abs(er)).max() < 1e-10
+    # and against the unsharded C-ABI step on the same inputs
+    c1, e1, v1 = ctx.ctmrgstep(bulk, c, e)
+    assert np.abs(vg - v1).max() < 1e-12 and np.abs(np.abs(cg) - np.abs(c1)).max() < 1e-11
+
+
+@pytest.mark.gpu
+def test_permute_and_svd_symmetrized_device_pointers(ctx):
+    import torch
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((5, 3, 4, 6))
+    dev = torch.device("cuda", ctx.device)
+    src = torch.from_numpy(np.ascontiguousarray(x.ravel(order="F"))).to(dev)
+    dst = torch.empty_like(src)
+    ctx.set_pointer_mode(1)
+    try:
+        ctx.dev_permute(src.data_ptr(), x.shape, (2, 0, 3, 1), dst.data_ptr())
+        n = 40
+        a = rng.standard_normal((n, n))
+        A = torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).to(dev)
+        U, S, V = torch.empty(n * n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n * n, dtype=torch.float64, device=dev)
+        ctx.dev_svd_symmetrized(A.data_ptr(), n, U.data_ptr(), S.data_ptr(), V.data_ptr())
+    finally:
+        ctx.set_pointer_mode(0)
+    got = dst.cpu().numpy().reshape((4, 5, 6, 3), order="F")
+    assert np.array_equal(got, np.transpose(x, (2, 0, 3, 1)))
+    u = U.cpu().numpy().reshape((n, n), order="F"); v = V.cpu().numpy().reshape((n, n), order="F"); s = S.cpu().numpy()
+    assert np.abs(u * s @ v.T - (a + a.T)).max() < 1e-12
+    assert np.abs(s - np.linalg.svd(a + a.T, compute_uv=False)).max() < 1e-12

@@ -220,3 +220,83 @@ def test_gloo_world2_replica_plumbing(tmp_path):
     assert all(x["max"] == 11.0 and x["sum"] == 3.0 for x in rows)
     got = sorted(i for x in rows for i in x["mine"])
     assert got == list(range(7))                      # every instance exactly once, no overlap
+
+
+# ---- chi-sharded ctmrgstep: the schedule (data) interpreted with NumPy under gloo, against the oracle --------------
+_SHARD_SCRIPT = r"""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import torch, torch.distributed as dist
+import tnad_oracle as O
+from tnad_b200.sharded import shard_plan, buffer_sizes, step_schedule
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+chi, d = 8, 2
+D = d * d
+rng = np.random.default_rng(5)
+a = rng.standard_normal((d, d, d, d, 2)); a = O.indexperm_symmetrize(a)
+bulk = O.double_layer(a)[1]
+corner = rng.standard_normal((chi, chi)); corner = corner + corner.T
+edge = rng.standard_normal((chi, D, chi)); edge = edge + edge.transpose(2, 1, 0)
+p = shard_plan(chi, D, world, rank)
+buf = {k: np.zeros(v) for k, v in buffer_sizes(p).items()}
+for k, v in (('bulk', bulk), ('corner', corner), ('edge', edge)):
+    buf[k][:] = v.ravel(order='F')
+view = lambda name, off, dims: buf[name][off:off + int(np.prod(dims))].reshape(dims, order='F')
+for op in step_schedule(p):
+    kind = op[0]
+    if kind == 'contract':
+        _, spec, (A, oa, da), (B, ob, db), out = op
+        r = np.einsum(spec, view(A, oa, da), view(B, ob, db))
+        buf[out][:r.size] = r.ravel(order='F')
+    elif kind == 'gather':
+        full, part = torch.from_numpy(buf[op[1]]), torch.from_numpy(buf[op[2]])
+        dist.all_gather_into_tensor(full, part)
+    elif kind == 'permute':
+        buf[op[4]][:] = np.transpose(view(op[1], 0, op[2]), op[3]).ravel(order='F')
+    elif kind == 'svd_symmetrized':
+        n = op[2]
+        M = view(op[1], 0, (n, n)); U, S, V = O.svd(M + M.T)
+        buf[op[3]][:] = U.ravel(order='F'); buf[op[4]][:] = S; buf[op[5]][:] = V.ravel(order='F')
+    elif kind == 'finish':
+        c1 = view(op[1], 0, (chi, chi)); e1 = view(op[2], 0, (chi, D, chi))
+        c2 = c1 + c1.T; e2 = e1 + e1.transpose(2, 1, 0)
+        buf[op[3]][:] = (c2 / np.linalg.norm(c2)).ravel(order='F'); buf[op[4]][:] = (e2 / np.linalg.norm(e2)).ravel(order='F')
+    else:
+        raise SystemExit('unknown op ' + kind)
+c_ref, e_ref, vals = O.ctmrgstep(bulk, corner, edge)
+c = view('corner_out', 0, (chi, chi)); e = view('edge_out', 0, (chi, D, chi))
+err = max(np.abs(c - c_ref).max(), np.abs(e - e_ref).max(), np.abs(buf['S'] / buf['S'][0] - vals).max())
+json.dump({'rank': rank, 'err': float(err), 'width': p.width, 'start': p.start}, open(os.path.join(OUT, 'r%d.json' % rank), 'w'))
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_shard_plan_rejects_uneven_split():
+    from tnad_b200.sharded import shard_plan, step_schedule, buffer_sizes
+    with pytest.raises(ValueError):
+        shard_plan(10, 4, 4, 0)
+    with pytest.raises(ValueError):
+        shard_plan(8, 4, 2, 2)
+    p = shard_plan(256, 25, 8, 3)
+    assert (p.width, p.start, p.n) == (32, 96, 6400)
+    names = set(buffer_sizes(p))
+    for op in step_schedule(p):          # every buffer the schedule touches exists, slices stay inside it
+        if op[0] == "contract":
+            for nm, off, dims in (op[2], op[3]):
+                assert nm in names and off + int(np.prod(dims)) <= buffer_sizes(p)[nm]
+            assert op[4] in names
+
+
+def test_gloo_world2_sharded_ctmrgstep_schedule(tmp_path):
+    script = tmp_path / "shard.py"
+    script.write_text(f"ROOT = {ROOT!r}\nOUT = {str(tmp_path)!r}\n" + _SHARD_SCRIPT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    rows = [json.load(open(tmp_path / f"r{k}.json")) for k in range(2)]
+    assert [x["start"] for x in rows] == [0, 4] and all(x["width"] == 4 for x in rows)
+    assert all(x["err"] < 1e-12 for x in rows), rows
