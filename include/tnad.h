@@ -143,6 +143,11 @@ TNAD_API int tnad_magnetisation_readout(tnad_ctx* ctx, const double* a, const do
 /* ---- pieces used by the chi-sharded multi-GPU step (tensornetworkad.jl_b200/sharded.py) -------- */
 /* svd(A + A') for a square A (ctmrg.jl:133-135: `cpmat += adjoint(cpmat); svd(cpmat)`), same solver as tnad_svd_sym */
 TNAD_API int tnad_svd_symmetrized(tnad_ctx* ctx, const double* A, int n, double* U, double* S, double* V, int* sweeps_out);
+/* stages of the direct symmetric eigensolver (tridiag.cu / stedc.cu), exported for the parity tests:
+   A = Q T Q' with T = tridiag(d, e) (Householder, LAPACK dsytrd semantics; Q explicit n x n) ... */
+TNAD_API int tnad_sytrd(tnad_ctx* ctx, const double* A, int n, double* d, double* e, double* Q);
+/* ... and all eigenpairs of tridiag(d, e), ascending (divide and conquer, LAPACK dstedc semantics) */
+TNAD_API int tnad_stedc(tnad_ctx* ctx, const double* d, const double* e, int n, double* lam, double* Z);
 /* permutedims(in, perm) (0-based perm, Julia semantics: out dim i = in dim perm[i]) */
 TNAD_API int tnad_permute(tnad_ctx* ctx, const double* in, const int64_t* dims, int rank, const int* perm, double* out);
 /* tail of ctmrgstep (ctmrg.jl:145-150): corner += corner', edge += permutedims(edge,(3,2,1)), each / its norm */

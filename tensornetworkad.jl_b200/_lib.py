@@ -62,6 +62,8 @@ SIGNATURES = {
                                              C.c_int, c_double_p]),
     "tnad_last_timing": (C.c_int, [C.c_void_p, c_double_p]),
     "tnad_svd_symmetrized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
+    "tnad_sytrd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tnad_stedc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_permute": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, c_int_p, C.c_void_p]),
     "tnad_ctmrg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
@@ -371,6 +373,21 @@ class Context:
                                         _p(g), C.byref(steps)))
         self.last_steps = steps.value
         return (e.value, g) if grad else e.value
+
+    def sytrd(self, a):
+        """A = Q tridiag(d, e) Q' (stage of the direct eigensolver)."""
+        a = farray(a)
+        n = a.shape[0]
+        d = np.empty(n); e = np.empty(max(n - 1, 1)); q = np.empty((n, n), order="F")
+        self.check(self.lib.tnad_sytrd(self.h, _p(a), n, _p(d), _p(e), _p(q)))
+        return d, e[:n - 1], q
+
+    def stedc(self, d, e):
+        d = np.ascontiguousarray(d, dtype=np.float64); e = np.ascontiguousarray(e, dtype=np.float64)
+        n = d.size
+        lam = np.empty(n); z = np.empty((n, n), order="F")
+        self.check(self.lib.tnad_stedc(self.h, _p(d), _p(e) if n > 1 else None, n, _p(lam), _p(z)))
+        return lam, z
 
     # ---- raw device-pointer calls (pointer mode DEVICE) used by sharded.py ---------------------------------
     def dev_contract(self, spec, pa, dims_a, pb, dims_b, pc, alpha=1.0, beta=0.0):

@@ -1,5 +1,7 @@
 // extern "C" surface of libtnad_b200.so (see include/tnad.h).  No exception crosses this boundary.
 #include "drivers.h"
+#include "eigdc.h"
+#include <algorithm>
 #include <mutex>
 
 using namespace tnad;
@@ -215,7 +217,7 @@ int tnad_svd_sym(tnad_ctx* c, const double* A, int n, double* U, double* S, doub
   TNAD_API_BEGIN(c)
   TNAD_REQUIRE(n >= 1, "tnad_svd_sym: empty matrix");
   Tens tA = t_in(c, A, {n, n});
-  SvdResult r = svd_symmetric(c, tA, false);
+  SvdResult r = svd_symmetric_auto(c, tA, false);
   t_out(c, r.U, U);
   t_out(c, r.S, S);
   t_out(c, r.V, V);
@@ -227,11 +229,60 @@ int tnad_svd_symmetrized(tnad_ctx* c, const double* A, int n, double* U, double*
   TNAD_API_BEGIN(c)
   TNAD_REQUIRE(n >= 1, "tnad_svd_symmetrized: empty matrix");
   Tens tA = t_in(c, A, {n, n});
-  SvdResult r = svd_symmetric(c, tA, true);
+  SvdResult r = svd_symmetric_auto(c, tA, true);
   t_out(c, r.U, U);
   t_out(c, r.S, S);
   t_out(c, r.V, V);
   if (sweeps_out) *sweeps_out = r.sweeps;
+  TNAD_API_END(c)
+}
+
+int tnad_sytrd(tnad_ctx* c, const double* A, int n, double* d, double* e, double* Q) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(n >= 1 && d && e && Q, "tnad_sytrd: bad arguments");
+  Tens tA = t_in(c, A, {n, n});
+  Tens Aw = t_clone(c, tA);
+  Tens Vh = t_alloc(c, {n, sytrd_vcols(n)}, true), tau = t_alloc(c, {sytrd_vcols(n)}, true), dd = t_alloc(c, {n}), ee = t_alloc(c, {n}, true);
+  sytrd(c, Aw.p, n, n, Vh.p, n, tau.p, dd.p, ee.p);
+  Tens Qm = t_alloc(c, {n, n}, true);
+  set_identity(c, Qm.p, n, n);
+  apply_q(c, Vh.p, n, tau.p, n, Qm.p, n, n);
+  t_out(c, dd, d);
+  if (n > 1) {
+    Tens ev = t_wrap(ee.p, {n - 1});
+    t_out(c, ev, e);
+  }
+  t_out(c, Qm, Q);
+  TNAD_API_END(c)
+}
+
+int tnad_stedc(tnad_ctx* c, const double* d, const double* e, int n, double* lam, double* Z) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(n >= 1 && d && lam && Z && (n == 1 || e), "tnad_stedc: bad arguments");
+  Tens td = t_in(c, d, {n});
+  Tens te = t_alloc(c, {n}, true);
+  if (n > 1) {
+    Tens tmp = t_in(c, e, {n - 1});
+    TNAD_CUDA(cudaMemcpyAsync(te.p, tmp.p, (size_t)(n - 1) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  Tens l, Zp;
+  int64_t N = 0;
+  stedc(c, td.p, te.p, n, l, Zp, N);
+  std::vector<double> lh((size_t)N);
+  d2h(c, lh.data(), l.p, (size_t)N);
+  std::vector<int> idx((size_t)N);
+  for (int64_t i = 0; i < N; ++i) idx[(size_t)i] = (int)i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lh[x] < lh[y]; });
+  Tens lo = t_alloc(c, {n}), Zo = t_alloc(c, {n, n});
+  std::vector<double> ls((size_t)n);
+  for (int j = 0; j < n; ++j) {
+    ls[(size_t)j] = lh[idx[(size_t)j]];
+    TNAD_CUDA(cudaMemcpyAsync(Zo.p + (int64_t)j * n, Zp.p + (int64_t)idx[(size_t)j] * N, (size_t)n * sizeof(double),
+                              cudaMemcpyDeviceToDevice, c->stream));
+  }
+  h2d(c, lo.p, ls.data(), (size_t)n);
+  t_out(c, lo, lam);
+  t_out(c, Zo, Z);
   TNAD_API_END(c)
 }
 

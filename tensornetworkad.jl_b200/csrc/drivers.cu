@@ -4,6 +4,7 @@
 // GEMM with permute-on-load (contract.cu / gemm.cu); the sequences below are the optimal-order,
 // `tp`-free association documented in DESIGN.md and mirrored one-to-one in oracle/tnad_oracle.py.
 #include "drivers.h"
+#include "eigdc.h"
 #include <cmath>
 #include <cstdlib>
 
@@ -242,7 +243,7 @@ void ctmrg_step(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& e
       svd = svd_jacobi(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);   // one-sided path (A/B switch)
       if (Vwarm) *Vwarm = svd.V;
     } else {
-      svd = svd_symmetric(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);
+      svd = svd_symmetric_auto(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);
       if (Vwarm) *Vwarm = svd.U;
     }
   }

@@ -1,0 +1,21 @@
+// Direct symmetric eigensolver: Householder tridiagonalisation (tridiag.cu) + divide and conquer (stedc.cu).
+#pragma once
+#include "common.h"
+
+namespace tnad {
+
+// A = Q T Q' (A overwritten; Vh zero-initialised n x n receives the reflectors; dd, ee: the tridiagonal T)
+void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t ldv, double* tau, double* dd, double* ee);
+int64_t sytrd_vcols(int64_t n);   // columns Vh / entries tau must provide (zero-initialised)
+// Z[0:n, 0:ncols] <- Q Z
+void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int64_t n, double* Z, int64_t ldz, int64_t ncols);
+// All eigenpairs of the symmetric tridiagonal (dd, ee) of order n.  The problem is padded to N = s 2^L >= n
+// (s <= 64) with decoupled diagonal entries above the spectrum; lam (N) and Z (N x N, leading dimension N) come
+// back unsorted, the pad eigenvalues being the N - n largest, their eigenvectors unit vectors in the pad rows.
+void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam, Tens& Z, int64_t& N);
+SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose);
+// Solver selection for symmetric inputs: TNAD_SYMEIG = 1 block Jacobi (symeig.cu), 2 tridiagonal divide and conquer;
+// default: divide and conquer from n >= TNAD_DC_MIN (256) on.
+SvdResult svd_symmetric_auto(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* Q0 = nullptr);
+
+}  // namespace tnad
