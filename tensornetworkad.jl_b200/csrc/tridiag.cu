@@ -251,6 +251,463 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel(double* A, long long l
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// One grid barrier per column (tools/sytrd1b_proto.py is the NumPy statement of the same data flow).
+// Index r (row and column) is owned by CTA r mod G; the owner keeps its rows of the panels V, W and of the running
+// vectors in shared memory.  Per column ONE exchange carries the matvec partials of A g (column ownership: CTA b
+// multiplies its own columns by its own entries of g), the panel dots with g and four scalars; the scalar of the
+// previous column that is still unknown when the matvec starts (c_p = tau_p^2 (y_p'v_p)/2) enters afterwards through
+//     x = g + 2 c_p v_p,   v = s (x - beta e),   A v = s (A g + 2 c_p (A v_p - A[:, j]) - beta A[:, jn]).
+// When the expansion of |x|^2 cancels (sig2 < theta * pieces) the column is redone with c_p folded in (one extra
+// barrier) so the backward error stays at the eps level on rank-deficient / graded matrices.
+constexpr int S1_NB = 32;   // panel width (lanes <-> panel columns)
+constexpr int S1_SS = 72;   // exchanged scalars per CTA: [0,32) V'g, [32,64) W'g, 64 gg, 65 gv, 66 vv, 67 y_p'v_p
+// Ownership in groups of 4 consecutive indices (one 32-byte sector of the exchange buffers): group q belongs to CTA
+// q mod G; local index l <-> row 4 (b + (l/4) G) + l%4.
+__device__ __forceinline__ int s1_row(int b, int G, int l) { return 4 * (b + (l >> 2) * G) + (l & 3); }
+__device__ __forceinline__ int s1_first(int b, int G, int x) {   // first local index whose row is >= x
+  if (x <= 0) return 0;
+  const int gx = x >> 2;
+  const int gl = gx > b ? (gx - b + G - 1) / G : 0;
+  return (b + gl * G == gx) ? 4 * gl + (x & 3) : 4 * gl;
+}
+__global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restrict__ A, long long lda, int n, int j0, int nbc,
+                                                           double* P1, double* P2, long long ldp, double* Vh, long long ldv,
+                                                           double* tau, double* dd, double* ee, double* upart, double* spart,
+                                                           double* pub, unsigned int* flags, unsigned int epoch0, int* err,
+                                                           double theta, int* redo_count, long long* prof) {
+  extern __shared__ double sm[];
+  const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int NQ = (n + 3) >> 2;                 // row quads
+  const int NL = 4 * ((NQ + G - 1) / G);
+  double* gs = sm;               // running column g (owned rows)
+  double* vps = gs + NL;         // previous reflector v_p
+  double* w0ps = vps + NL;       // tau_p y_p
+  double* yps = w0ps + NL;       // y_p
+  double* avps = yps + NL;       // A v_p
+  double* us = avps + NL;        // (A g) summed over CTAs
+  double* ajs = us + NL;         // A[r, j]
+  double* ajns = ajs + NL;       // A[r, jn]
+  double* Vs = ajns + NL;        // NL x 32
+  double* Ws = Vs + NL * S1_NB;  // NL x 32
+  double* sums = Ws + NL * S1_NB;   // 80
+  double* sv = sums + 80;
+  double* sw = sv + S1_NB;
+  double* svp = sw + S1_NB;
+  double* swp = svp + S1_NB;
+  double* vjn = swp + S1_NB;     // V[jn, :]
+  double* wjn = vjn + S1_NB;     // W[jn, :] (final values)
+  double* vjr = wjn + S1_NB;     // V[j, :]
+  double* wjr = vjr + S1_NB;     // W[j, :]
+  double* misc = wjr + S1_NB;    // 24
+  __shared__ int s_to;
+  double* gpub = pub;                   // [2][n]
+  double* apub = pub + 2 * (long long)n;
+  double* wpub = pub + 4 * (long long)n;
+  unsigned int epoch = epoch0, xc = 0;
+  const int NLb = s1_first(b, G, n);           // owned rows with r < n
+  const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<unsigned long long>(A) & 15ull) == 0);
+  if (t == 0) s_to = 0;
+  for (int l = t; l < NL; l += ST_NT) {
+    const int r = s1_row(b, G, l);
+    gs[l] = (r > j0 && r < n) ? A[r + (long long)j0 * lda] : 0.0;
+    vps[l] = w0ps[l] = yps[l] = avps[l] = us[l] = ajs[l] = ajns[l] = 0.0;
+  }
+  for (int q = t; q < NL * S1_NB; q += ST_NT) Vs[q] = Ws[q] = 0.0;
+  if (t < S1_NB) svp[t] = swp[t] = 0.0;
+  __syncthreads();
+
+  int i = 0;
+  bool pending = false;
+  double tau_p = 0.0;
+  long long tprev = clock64();
+#define S1_PROF(slot)                                            \
+  if (prof && b == 0 && t == 0) {                                \
+    const long long tn = clock64();                              \
+    prof[slot] += tn - tprev;                                    \
+    tprev = tn;                                                  \
+  }
+  for (;;) {
+    const bool fin = (i == nbc);
+    const int j = j0 + i, jn = j + 1;
+    const int par = (int)(xc & 1u);
+    ++xc;
+    const int lmin = s1_first(b, G, jn);        // first owned local row with r >= jn
+    const int lminj = s1_first(b, G, j);        // ... with r >= j
+    // ---------------- pre-barrier ----------------
+    if (!fin) {
+      // matvec partial on row quads: u_b[4q..4q+3] = sum over owned columns c >= jn of A[4q.., c] g[c]
+      double* up = upart + (long long)par * NQ * G * 4;
+      for (int q = (jn >> 2) + t; q < NQ; q += ST_NT) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const int r0 = 4 * q;
+        if (vec_ok && r0 + 3 < n) {
+#pragma unroll 8
+          for (int l = lmin; l < NLb; ++l) {
+            const double2* col = reinterpret_cast<const double2*>(A + (long long)s1_row(b, G, l) * lda + r0);
+            const double gl = gs[l];
+            const double2 x0 = col[0], x1 = col[1];
+            a0 += x0.x * gl;
+            a1 += x0.y * gl;
+            a2 += x1.x * gl;
+            a3 += x1.y * gl;
+          }
+        } else {
+          for (int l = lmin; l < NLb; ++l) {
+            const double* col = A + (long long)s1_row(b, G, l) * lda + r0;
+            const double gl = gs[l];
+            a0 += col[0] * gl;
+            if (r0 + 1 < n) a1 += col[1] * gl;
+            if (r0 + 2 < n) a2 += col[2] * gl;
+            if (r0 + 3 < n) a3 += col[3] * gl;
+          }
+        }
+        double2* dst = reinterpret_cast<double2*>(up + ((long long)q * G + b) * 4);
+        dst[0] = make_double2(a0, a1);
+        dst[1] = make_double2(a2, a3);
+      }
+      S1_PROF(0)
+      for (int l = lmin + t; l < NLb; l += ST_NT) {
+        const int r = s1_row(b, G, l);
+        ajs[l] = A[r + (long long)j * lda];
+        ajns[l] = A[r + (long long)jn * lda];
+      }
+      for (int l = lminj + t; l < NLb; l += ST_NT) {
+        const int r = s1_row(b, G, l);
+        gpub[(long long)par * n + r] = gs[l];
+        apub[(long long)par * n + r] = avps[l];
+        wpub[(long long)par * n + r] = w0ps[l];
+      }
+    }
+    {
+      // partial sums over owned rows: 4 lanes per slot (272 threads), two shuffle steps
+      const int l1 = s1_first(b, G, jn + 1);      // rows > jn
+      double* sp = spart + (long long)par * S1_SS * G;
+      const int slot = t >> 2, part = t & 3;
+      if (t < 288) {   // warps 0..8 (slots 68..71 are idle lanes that only take part in the shuffles)
+        double s = 0.0;
+        bool need = slot < 68;
+        if (slot >= 68) {
+        } else if (slot < 64) {
+          const int k = slot & 31;
+          need = !fin && k < i;
+          if (need) {
+            const double* X = (slot < 32) ? Vs : Ws;
+            for (int l = lmin + part; l < NLb; l += 4) s += X[l * S1_NB + k] * gs[l];
+          }
+        } else if (slot == 64) {
+          for (int l = l1 + part; l < NLb; l += 4) s += gs[l] * gs[l];
+        } else if (slot == 65) {
+          for (int l = l1 + part; l < NLb; l += 4) s += gs[l] * vps[l];
+        } else if (slot == 66) {
+          for (int l = l1 + part; l < NLb; l += 4) s += vps[l] * vps[l];
+        } else {
+          for (int l = lminj + part; l < NLb; l += 4) s += yps[l] * vps[l];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (need && part == 0) sp[(long long)slot * G + b] = s;
+      }
+    }
+    S1_PROF(1)
+    grid_barrier(flags, ++epoch, G, err, &s_to);
+    S1_PROF(2)
+    // ---------------- post-barrier: gather.  All loads are issued from fully unrolled register arrays before the
+    // first reduction, so the phase costs one L2 round trip (G <= 160). ----------------
+    {
+      const double* sp = spart + (long long)par * S1_SS * G;
+      const double* up = upart + (long long)par * NQ * G * 4;
+      // round A (all threads): slots 0..63 = V'g, W'g, 8 lanes per slot
+      const int slotA = t >> 3, partA = t & 7;
+      const bool needA = !fin && (slotA & 31) < i;
+      double xa[20];
+#pragma unroll
+      for (int u = 0; u < 20; ++u) {
+        const int q = partA + 8 * u;
+        xa[u] = (needA && q < G) ? __ldcg(sp + (long long)slotA * G + q) : 0.0;
+      }
+      // round B: threads 0..31 the four scalars (8 lanes each), warp 1 u[jn], warps 2.. the owned quads (one warp
+      // per quad), the last threads the rows jn / j of the panels and the published scalars
+      double xb[20];
+      const int glq = (lmin >> 2) + (warp - 2);
+      const bool quadw = !fin && warp >= 2 && 4 * glq < NLb;
+#pragma unroll
+      for (int u = 0; u < 20; ++u) xb[u] = 0.0;
+      if (t < 32) {
+        const int slotB = 64 + (t >> 3);
+#pragma unroll
+        for (int u = 0; u < 20; ++u) {
+          const int q = (t & 7) + 8 * u;
+          if (q < G) xb[u] = __ldcg(sp + (long long)slotB * G + q);
+        }
+      } else if (t < 64) {
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int q = lane + 32 * u;
+          if (!fin && q < G) xb[u] = __ldcg(up + ((long long)(jn >> 2) * G + q) * 4 + (jn & 3));
+        }
+      } else if (quadw) {
+        const int qd = b + glq * G;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int q = lane + 32 * u;
+          if (q < G) {
+            const double2* src = reinterpret_cast<const double2*>(up + ((long long)qd * G + q) * 4);
+            const double2 y0 = __ldcg(src), y1 = __ldcg(src + 1);
+            xb[4 * u] = y0.x;
+            xb[4 * u + 1] = y0.y;
+            xb[4 * u + 2] = y1.x;
+            xb[4 * u + 3] = y1.y;
+          }
+        }
+      }
+      if (!fin) {
+        const int tt = ST_NT - 1 - t;
+        if (tt < i) {
+          vjn[tt] = __ldcg(P1 + jn + (long long)tt * ldp);
+          vjr[tt] = __ldcg(P1 + j + (long long)tt * ldp);
+          const bool stale = pending && tt == i - 1;    // W column i-1 is not final yet: use the published w0_p
+          wjn[tt] = stale ? 0.0 : __ldcg(P1 + jn + (long long)(S1_NB + tt) * ldp);
+          wjr[tt] = stale ? 0.0 : __ldcg(P1 + j + (long long)(S1_NB + tt) * ldp);
+        }
+        if (tt == 32) misc[0] = __ldcg(gpub + (long long)par * n + jn);
+        if (tt == 33) misc[1] = __ldcg(wpub + (long long)par * n + jn);
+        if (tt == 34) misc[2] = __ldcg(wpub + (long long)par * n + j);
+        if (tt == 35) misc[3] = __ldcg(apub + (long long)par * n + jn);
+        if (tt == 36) misc[4] = A[jn + (long long)j * lda];
+        if (tt == 37) misc[5] = A[jn + (long long)jn * lda];
+        if (tt == 38) misc[6] = A[j + (long long)j * lda];
+        if (tt == 39) misc[7] = (pending && i > 0) ? __ldcg(P1 + jn + (long long)(i - 1) * ldp) : 0.0;   // v_p[jn]
+      }
+      // reductions
+      {
+        double sA = 0.0;
+#pragma unroll
+        for (int u = 0; u < 20; ++u) sA += xa[u];
+        sA += __shfl_xor_sync(0xffffffffu, sA, 1);
+        sA += __shfl_xor_sync(0xffffffffu, sA, 2);
+        sA += __shfl_xor_sync(0xffffffffu, sA, 4);
+        if (needA && partA == 0) sums[slotA] = sA;
+      }
+      if (t < 32) {
+        double sB = 0.0;
+#pragma unroll
+        for (int u = 0; u < 20; ++u) sB += xb[u];
+        sB += __shfl_xor_sync(0xffffffffu, sB, 1);
+        sB += __shfl_xor_sync(0xffffffffu, sB, 2);
+        sB += __shfl_xor_sync(0xffffffffu, sB, 4);
+        if ((t & 7) == 0) sums[64 + (t >> 3)] = sB;
+      } else if (t < 64) {
+        double sB = (xb[0] + xb[1]) + (xb[2] + xb[3]) + xb[4];
+        sB = warp_sum(sB);
+        if (lane == 0) misc[8] = sB;   // u[jn]
+      } else if (quadw) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          s0 += xb[4 * u];
+          s1 += xb[4 * u + 1];
+          s2 += xb[4 * u + 2];
+          s3 += xb[4 * u + 3];
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        s3 = warp_sum(s3);
+        if (lane == 0) {
+          us[4 * glq] = s0;
+          us[4 * glq + 1] = s1;
+          us[4 * glq + 2] = s2;
+          us[4 * glq + 3] = s3;
+        }
+      }
+      // more owned quads than warps (n > ~8000): the rest, one warp per quad
+      if (!fin) {
+        for (int gl = (lmin >> 2) + (ST_NW - 2) + warp; 4 * gl < NLb; gl += ST_NW) {
+          const int qd = b + gl * G;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          for (int q = lane; q < G; q += 32) {
+            const double2* src = reinterpret_cast<const double2*>(up + ((long long)qd * G + q) * 4);
+            const double2 y0 = __ldcg(src), y1 = __ldcg(src + 1);
+            s0 += y0.x;
+            s1 += y0.y;
+            s2 += y1.x;
+            s3 += y1.y;
+          }
+          s0 = warp_sum(s0);
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          s3 = warp_sum(s3);
+          if (lane == 0) {
+            us[4 * gl] = s0;
+            us[4 * gl + 1] = s1;
+            us[4 * gl + 2] = s2;
+            us[4 * gl + 3] = s3;
+          }
+        }
+      }
+    }
+    if (fin) {
+      __syncthreads();
+      const double c_l = 0.5 * tau_p * tau_p * sums[67];
+      for (int l = lminj + t; l < NLb; l += ST_NT) {
+        const int r = s1_row(b, G, l);
+        const double w = w0ps[l] - c_l * vps[l];
+        P1[r + (long long)(S1_NB + nbc - 1) * ldp] = w;
+        P2[r + (long long)(nbc - 1) * ldp] = w;
+      }
+      break;
+    }
+    __syncthreads();
+    S1_PROF(3)
+    // ---------------- global scalars: one thread does the divisions / square root, everybody reads them ----------
+    if (t == 0) {
+      const double gam = sums[67], gg = sums[64], gv = sums[65], vv = sums[66];
+      const double cp = pending ? 0.5 * tau_p * tau_p * gam : 0.0;
+      const double al = misc[0] + 2.0 * cp * misc[7];
+      const double sg2 = gg + 4.0 * cp * gv + 4.0 * cp * cp * vv;
+      double be, tq, sq, rd = 0.0;
+      if (pending && sg2 < theta * (gg + 4.0 * cp * cp * vv)) {
+        rd = 1.0;
+        be = tq = sq = 0.0;
+      } else if (!(sg2 > 0.0)) {
+        be = al;
+        tq = 0.0;
+        sq = 0.0;
+      } else {
+        be = -copysign(sqrt(al * al + sg2), al);
+        tq = (be - al) / be;
+        sq = 1.0 / (al - be);
+      }
+      misc[10] = cp;
+      misc[11] = be;
+      misc[12] = tq;
+      misc[13] = sq;
+      misc[14] = rd;
+    }
+    __syncthreads();
+    const double gam_p = sums[67], s_gv = sums[65], s_vv = sums[66];
+    const double g_jn = misc[0], w0p_jn = misc[1], w0p_j = misc[2], avp_jn = misc[3], A_jn_j = misc[4], A_jn_jn = misc[5],
+                 A_j_j = misc[6], vp_jn = misc[7], u_jn = misc[8];
+    const double c_p = misc[10], beta = misc[11], tj = misc[12], s = misc[13];
+    if (misc[14] != 0.0) {
+      // cancellation: fold c_p in, finish W column i-1, redo this column's exchange with nothing pending
+      for (int l = lminj + t; l < NLb; l += ST_NT) {
+        const int r = s1_row(b, G, l);
+        const double w = w0ps[l] - c_p * vps[l];
+        Ws[l * S1_NB + (i - 1)] = w;
+        P1[r + (long long)(S1_NB + i - 1) * ldp] = w;
+        P2[r + (long long)(i - 1) * ldp] = w;
+        gs[l] = (r >= jn) ? gs[l] + 2.0 * c_p * vps[l] : 0.0;
+      }
+      if (b == 0 && t == 0) atomicAdd(redo_count, 1);
+      pending = false;
+      __syncthreads();
+      continue;
+    }
+    if (t < i) {
+      const int k = t;
+      double Vk_vp, Wk_vp, Wk_g, Wk_jn, Wk_j;
+      if (k < i - 1 || !pending) {
+        Vk_vp = svp[k] - vjr[k];
+        Wk_vp = swp[k] - wjr[k];
+        Wk_g = sums[32 + k];
+        Wk_jn = wjn[k];
+        Wk_j = wjr[k];
+      } else {
+        const double vv = s_vv + vp_jn * vp_jn, gv = s_gv + g_jn * vp_jn;
+        Vk_vp = vv;
+        Wk_vp = (tau_p * gam_p - w0p_j) - c_p * vv;
+        Wk_g = sums[32 + k] - c_p * gv;
+        Wk_jn = w0p_jn - c_p * vp_jn;
+        Wk_j = w0p_j - c_p;
+      }
+      const double tv = pending ? 2.0 * c_p * Vk_vp : 0.0, tw = pending ? 2.0 * c_p * Wk_vp : 0.0;
+      if (s != 0.0) {
+        sv[k] = s * (sums[k] + tv - beta * vjn[k]);
+        sw[k] = s * (Wk_g + tw - beta * Wk_jn);
+      } else {
+        sv[k] = vjn[k];
+        sw[k] = Wk_jn;
+      }
+      wjn[k] = Wk_jn;
+      wjr[k] = Wk_j;
+    }
+    __syncthreads();
+    S1_PROF(4)
+    if (warp == 0) {
+      double a = 0.0, q = 0.0;
+      if (lane < i) {
+        a = vjr[lane] * wjr[lane];
+        q = vjn[lane] * sw[lane] + wjn[lane] * sv[lane];
+      }
+      a = warp_sum(a);
+      q = warp_sum(q);
+      if (lane == 0) {
+        const double Av_jn = (s != 0.0) ? s * (u_jn + 2.0 * c_p * (avp_jn - A_jn_j) - beta * A_jn_jn) : A_jn_jn;
+        misc[9] = tj * (Av_jn - q);       // w0[jn]
+        if (b == 0) {
+          dd[j] = A_j_j - 2.0 * a;
+          ee[j] = beta;
+          tau[j] = tj;
+        }
+      }
+    }
+    __syncthreads();
+    S1_PROF(5)
+    const double w0_jn = misc[9];
+    // ---------------- owned rows: finish W column i-1, new v / y / w0, next g ----------------
+    for (int l = lmin + warp; l < NLb; l += ST_NW) {
+      const int r = s1_row(b, G, l);
+      double vk = 0.0, wk = 0.0;
+      if (lane < i) {
+        vk = Vs[l * S1_NB + lane];
+        wk = Ws[l * S1_NB + lane];
+        if (pending && lane == i - 1) wk = w0ps[l] - c_p * vps[l];
+      }
+      const double x = gs[l] + 2.0 * c_p * vps[l];
+      const double v = (r == jn) ? 1.0 : s * x;
+      const double Av = (s != 0.0) ? s * (us[l] + 2.0 * c_p * (avps[l] - ajs[l]) - beta * ajns[l]) : ajns[l];
+      double acc = 0.0, acc2 = 0.0;
+      if (lane < i) {
+        acc = vk * sw[lane] + wk * sv[lane];
+        acc2 = vk * wjn[lane] + wk * vjn[lane];
+      }
+      acc = warp_sum(acc);
+      acc2 = warp_sum(acc2);
+      const double y = Av - acc, w0 = tj * y;
+      const double gnew = (r > jn) ? (ajns[l] - acc2) - v * w0_jn - w0 : 0.0;
+      __syncwarp();
+      if (pending && lane == i - 1) {
+        Ws[l * S1_NB + lane] = wk;
+        P1[r + (long long)(S1_NB + lane) * ldp] = wk;
+        P2[r + (long long)lane * ldp] = wk;
+      }
+      if (lane == 0) {
+        Vs[l * S1_NB + i] = v;
+        Ws[l * S1_NB + i] = w0;
+        vps[l] = v;
+        w0ps[l] = w0;
+        yps[l] = y;
+        avps[l] = Av;
+        gs[l] = gnew;
+        P1[r + (long long)i * ldp] = v;
+        P2[r + (long long)(S1_NB + i) * ldp] = v;
+        Vh[r + (long long)j * ldv] = v;
+      }
+    }
+    if (t < S1_NB) {
+      svp[t] = (t < i) ? sv[t] : 0.0;
+      swp[t] = (t < i) ? sw[t] : 0.0;
+    }
+    tau_p = tj;
+    pending = true;
+    ++i;
+    __syncthreads();
+    S1_PROF(6)
+  }
+}
+
 __global__ void k_sytrd_tail(const double* A, long long lda, int n, double* dd, double* ee) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (n >= 2) {
@@ -346,6 +803,21 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     TNAD_REQUIRE(per_sm >= 1, "sytrd: panel kernel does not fit on an SM");
     const int G = c->num_sms;
     const int64_t ldp = n;
+    const bool one_barrier = env_i("TNAD_SYTRD_1B", 1) != 0;
+    const int64_t NQ = (n + 3) / 4, NL = 4 * ((NQ + G - 1) / G);
+    const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 8 * S1_NB + 24) * sizeof(double);
+    Tens upart, spart1, pub, redo, prof;
+    double theta = 0.1;
+    if (const char* ev = getenv("TNAD_SYTRD_THETA")) theta = atof(ev);
+    if (one_barrier) {
+      TNAD_REQUIRE(smem1 <= 200 * 1024, "sytrd: matrix too large");
+      TNAD_CUDA(cudaFuncSetAttribute(k_sytrd_panel1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      upart = t_alloc(c, {4 * NQ, (int64_t)G, 2});
+      spart1 = t_alloc(c, {S1_SS, (int64_t)G, 2}, true);
+      pub = t_alloc(c, {n, 6}, true);
+      redo = t_alloc(c, {2}, true);
+      prof = t_alloc(c, {8}, true);
+    }
     Tens P1 = t_alloc(c, {ldp, 2 * nb}, true), P2 = t_alloc(c, {ldp, 2 * nb}, true);
     const int64_t nchmax = (n + ST_CH - 1) / ST_CH;
     Tens ppart = t_alloc(c, {n, nchmax}), spart = t_alloc(c, {2 * nb, nchmax}), pvpart = t_alloc(c, {G});
@@ -360,12 +832,18 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       long long lda_ = lda, ldp_ = ldp, ldv_ = ldv;
       double *P1p = P1.p, *P2p = P2.p, *pp = ppart.p, *sp = spart.p, *pvp = pvpart.p;
       void* args[] = {&A, &lda_, &ni, &j0i, &nbc, &nbi, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &pp, &sp, &pvp, &bar, &bar_base, &err, &dbg};
+      const double* Ac = A;
+      double *upp = upart.p, *spp = spart1.p, *pubp = pub.p;
+      int* redop = reinterpret_cast<int*>(redo.p);
+      long long* profp = env_i("TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(prof.p) : nullptr;
+      void* args1[] = {&Ac, &lda_, &ni, &j0i, &nbc, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &upp, &spp, &pubp, &bar, &bar_base, &err, &theta, &redop, &profp};
       {
         KTimer kt(c, KF_EIG);
-        TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(G), dim3(ST_NT), args, smem, st));
+        if (one_barrier) TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel1, dim3(G), dim3(ST_NT), args1, smem1, st));
+        else TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(G), dim3(ST_NT), args, smem, st));
       }
       c->launches++;
-      bar_base += (unsigned int)(2 * nbc);   // barrier epochs consumed by this launch
+      bar_base += (unsigned int)(2 * nbc + 2);   // barrier epochs this launch may consume
       // trailing update A22 -= [V W] [W V]'
       const int64_t jt = j0 + nbc, nt = n - jt;
       if (nt > 0) {
@@ -384,6 +862,16 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     TNAD_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     sync(c);
     if (herr) fail(TNAD_ERR_INTERNAL, "sytrd: grid barrier timed out");
+    if (one_barrier && env_i("TNAD_DC_DEBUG", 0)) {
+      int rc = 0;
+      TNAD_CUDA(cudaMemcpy(&rc, redo.p, sizeof(int), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[tnad dc] sytrd: %d of %lld columns redone (cancellation guard, theta %.3g)\n", rc, (long long)nref, theta);
+      long long ph[8];
+      TNAD_CUDA(cudaMemcpy(ph, prof.p, sizeof(ph), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[tnad dc] sytrd CTA0 cycles/column: matvec %.0f  sums+publish %.0f  barrier %.0f  gather %.0f  scalars %.0f  warp0 %.0f  rows %.0f\n",
+              (double)ph[0] / nref, (double)ph[1] / nref, (double)ph[2] / nref, (double)ph[3] / nref, (double)ph[4] / nref,
+              (double)ph[5] / nref, (double)ph[6] / nref);
+    }
   }
   k_sytrd_tail<<<1, 32, 0, st>>>(A, lda, (int)n, dd, ee);
   c->launches++;
