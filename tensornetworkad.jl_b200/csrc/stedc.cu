@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256) k_dc_rot_s(int m2, const int* __restrict_
 
 void leaf_plan(int64_t n, int& s, int& L) {
   const char* ev = getenv("TNAD_DC_LEAF");
-  const int smax = ev ? std::max(4, std::min(64, atoi(ev))) : 32;
+  const int smax = ev ? std::max(4, std::min(64, atoi(ev))) : 16;   // measured at n = 2048: 16 -> 2.2 ms, 32 -> 2.5, 64 -> 4.9
   L = 0;
   while ((n + (1LL << L) - 1) / (1LL << L) > smax) ++L;
   s = (int)((n + (1LL << L) - 1) / (1LL << L));

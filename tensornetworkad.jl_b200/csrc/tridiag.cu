@@ -293,9 +293,9 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
   double* sums = Ws + NL * S1_NB;   // 80
   double* sv = sums + 80;
   double* sw = sv + S1_NB;
-  double* svp = sw + S1_NB;
-  double* swp = svp + S1_NB;
-  double* vjn = swp + S1_NB;     // V[jn, :]
+  double* svp = sw + S1_NB;      // [2][32] (column parity)
+  double* swp = svp + 2 * S1_NB; // [2][32]
+  double* vjn = swp + 2 * S1_NB; // V[jn, :]
   double* wjn = vjn + S1_NB;     // W[jn, :] (final values)
   double* vjr = wjn + S1_NB;     // V[j, :]
   double* wjr = vjr + S1_NB;     // W[j, :]
@@ -311,10 +311,12 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
   for (int l = t; l < NL; l += ST_NT) {
     const int r = s1_row(b, G, l);
     gs[l] = (r > j0 && r < n) ? A[r + (long long)j0 * lda] : 0.0;
-    vps[l] = w0ps[l] = yps[l] = avps[l] = us[l] = ajs[l] = ajns[l] = 0.0;
+    vps[l] = w0ps[l] = yps[l] = avps[l] = us[l] = 0.0;
+    ajs[l] = (r < n) ? A[r + (long long)j0 * lda] : 0.0;
+    ajns[l] = (r < n && j0 + 1 < n) ? A[r + (long long)(j0 + 1) * lda] : 0.0;
   }
   for (int q = t; q < NL * S1_NB; q += ST_NT) Vs[q] = Ws[q] = 0.0;
-  if (t < S1_NB) svp[t] = swp[t] = 0.0;
+  if (t < 2 * S1_NB) svp[t] = swp[t] = 0.0;
   __syncthreads();
 
   int i = 0;
@@ -367,11 +369,6 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
         dst[1] = make_double2(a2, a3);
       }
       S1_PROF(0)
-      for (int l = lmin + t; l < NLb; l += ST_NT) {
-        const int r = s1_row(b, G, l);
-        ajs[l] = A[r + (long long)j * lda];
-        ajns[l] = A[r + (long long)jn * lda];
-      }
       for (int l = lminj + t; l < NLb; l += ST_NT) {
         const int r = s1_row(b, G, l);
         gpub[(long long)par * n + r] = gs[l];
@@ -560,24 +557,29 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
     }
     __syncthreads();
     S1_PROF(3)
-    // ---------------- global scalars: one thread does the divisions / square root, everybody reads them ----------
+    // ---------------- global scalars and panel dots, redundantly in every warp (lane k <-> panel column k): no
+    // block-wide synchronisation between the gather and the row updates ----------------
+    const double gam_p = sums[67], s_gv = sums[65], s_vv = sums[66];
+    const double g_jn = misc[0], w0p_jn = misc[1], w0p_j = misc[2], avp_jn = misc[3], A_jn_j = misc[4], A_jn_jn = misc[5],
+                 A_j_j = misc[6], vp_jn = misc[7], u_jn = misc[8];
+    // one thread does the square root and the division (FP64 issue is per warp instruction: doing this in all
+    // 16 warps costs more than the extra __syncthreads)
     if (t == 0) {
-      const double gam = sums[67], gg = sums[64], gv = sums[65], vv = sums[66];
-      const double cp = pending ? 0.5 * tau_p * tau_p * gam : 0.0;
-      const double al = misc[0] + 2.0 * cp * misc[7];
-      const double sg2 = gg + 4.0 * cp * gv + 4.0 * cp * cp * vv;
-      double be, tq, sq, rd = 0.0;
-      if (pending && sg2 < theta * (gg + 4.0 * cp * cp * vv)) {
+      const double gg = sums[64];
+      const double cp = pending ? 0.5 * tau_p * tau_p * gam_p : 0.0;
+      const double al = g_jn + 2.0 * cp * vp_jn;
+      const double sg2 = gg + 4.0 * cp * s_gv + 4.0 * cp * cp * s_vv;
+      double be = 0.0, tq = 0.0, sq = 0.0, rd = 0.0;
+      if (pending && sg2 < theta * (gg + 4.0 * cp * cp * s_vv)) {
         rd = 1.0;
-        be = tq = sq = 0.0;
       } else if (!(sg2 > 0.0)) {
         be = al;
-        tq = 0.0;
-        sq = 0.0;
       } else {
         be = -copysign(sqrt(al * al + sg2), al);
-        tq = (be - al) / be;
-        sq = 1.0 / (al - be);
+        const double amb = al - be;
+        const double rr = 1.0 / (be * amb);     // one division: 1/(alpha-beta) = rr*beta, 1/beta = rr*(alpha-beta)
+        sq = rr * be;
+        tq = -amb * (rr * amb);
       }
       misc[10] = cp;
       misc[11] = be;
@@ -586,12 +588,10 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
       misc[14] = rd;
     }
     __syncthreads();
-    const double gam_p = sums[67], s_gv = sums[65], s_vv = sums[66];
-    const double g_jn = misc[0], w0p_jn = misc[1], w0p_j = misc[2], avp_jn = misc[3], A_jn_j = misc[4], A_jn_jn = misc[5],
-                 A_j_j = misc[6], vp_jn = misc[7], u_jn = misc[8];
-    const double c_p = misc[10], beta = misc[11], tj = misc[12], s = misc[13];
-    if (misc[14] != 0.0) {
+    const double c_p = misc[10], beta = misc[11], tj = misc[12], s = misc[13], rdo = misc[14];
+    if (rdo != 0.0) {
       // cancellation: fold c_p in, finish W column i-1, redo this column's exchange with nothing pending
+      __syncthreads();
       for (int l = lminj + t; l < NLb; l += ST_NT) {
         const int r = s1_row(b, G, l);
         const double w = w0ps[l] - c_p * vps[l];
@@ -605,57 +605,47 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
       __syncthreads();
       continue;
     }
-    if (t < i) {
-      const int k = t;
-      double Vk_vp, Wk_vp, Wk_g, Wk_jn, Wk_j;
+    const double* svq = svp + (i & 1) * S1_NB;
+    const double* swq = swp + (i & 1) * S1_NB;
+    double sv_k = 0.0, sw_k = 0.0, vjn_k = 0.0, wjn_k = 0.0, vjr_k = 0.0, wjr_k = 0.0;
+    if (lane < i) {
+      const int k = lane;
+      vjn_k = vjn[k];
+      vjr_k = vjr[k];
+      double Vk_vp, Wk_vp, Wk_g;
       if (k < i - 1 || !pending) {
-        Vk_vp = svp[k] - vjr[k];
-        Wk_vp = swp[k] - wjr[k];
+        Vk_vp = svq[k] - vjr_k;
+        Wk_vp = swq[k] - wjr[k];
         Wk_g = sums[32 + k];
-        Wk_jn = wjn[k];
-        Wk_j = wjr[k];
+        wjn_k = wjn[k];
+        wjr_k = wjr[k];
       } else {
         const double vv = s_vv + vp_jn * vp_jn, gv = s_gv + g_jn * vp_jn;
         Vk_vp = vv;
         Wk_vp = (tau_p * gam_p - w0p_j) - c_p * vv;
         Wk_g = sums[32 + k] - c_p * gv;
-        Wk_jn = w0p_jn - c_p * vp_jn;
-        Wk_j = w0p_j - c_p;
+        wjn_k = w0p_jn - c_p * vp_jn;
+        wjr_k = w0p_j - c_p;
       }
       const double tv = pending ? 2.0 * c_p * Vk_vp : 0.0, tw = pending ? 2.0 * c_p * Wk_vp : 0.0;
       if (s != 0.0) {
-        sv[k] = s * (sums[k] + tv - beta * vjn[k]);
-        sw[k] = s * (Wk_g + tw - beta * Wk_jn);
+        sv_k = s * (sums[k] + tv - beta * vjn_k);
+        sw_k = s * (Wk_g + tw - beta * wjn_k);
       } else {
-        sv[k] = vjn[k];
-        sw[k] = Wk_jn;
+        sv_k = vjn_k;
+        sw_k = wjn_k;
       }
-      wjn[k] = Wk_jn;
-      wjr[k] = Wk_j;
     }
-    __syncthreads();
+    const double a_d = warp_sum(vjr_k * wjr_k);
+    const double q_y = warp_sum(vjn_k * sw_k + wjn_k * sv_k);
+    const double Av_jn = (s != 0.0) ? s * (u_jn + 2.0 * c_p * (avp_jn - A_jn_j) - beta * A_jn_jn) : A_jn_jn;
+    const double w0_jn = tj * (Av_jn - q_y);
+    if (b == 0 && t == 0) {
+      dd[j] = A_j_j - 2.0 * a_d;
+      ee[j] = beta;
+      tau[j] = tj;
+    }
     S1_PROF(4)
-    if (warp == 0) {
-      double a = 0.0, q = 0.0;
-      if (lane < i) {
-        a = vjr[lane] * wjr[lane];
-        q = vjn[lane] * sw[lane] + wjn[lane] * sv[lane];
-      }
-      a = warp_sum(a);
-      q = warp_sum(q);
-      if (lane == 0) {
-        const double Av_jn = (s != 0.0) ? s * (u_jn + 2.0 * c_p * (avp_jn - A_jn_j) - beta * A_jn_jn) : A_jn_jn;
-        misc[9] = tj * (Av_jn - q);       // w0[jn]
-        if (b == 0) {
-          dd[j] = A_j_j - 2.0 * a;
-          ee[j] = beta;
-          tau[j] = tj;
-        }
-      }
-    }
-    __syncthreads();
-    S1_PROF(5)
-    const double w0_jn = misc[9];
     // ---------------- owned rows: finish W column i-1, new v / y / w0, next g ----------------
     for (int l = lmin + warp; l < NLb; l += ST_NW) {
       const int r = s1_row(b, G, l);
@@ -669,9 +659,11 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
       const double v = (r == jn) ? 1.0 : s * x;
       const double Av = (s != 0.0) ? s * (us[l] + 2.0 * c_p * (avps[l] - ajs[l]) - beta * ajns[l]) : ajns[l];
       double acc = 0.0, acc2 = 0.0;
+      double a_next = 0.0;
+      if (lane == 1 && jn + 1 < n) a_next = A[r + (long long)(jn + 1) * lda];   // A[r, jn+1] for the next column
       if (lane < i) {
-        acc = vk * sw[lane] + wk * sv[lane];
-        acc2 = vk * wjn[lane] + wk * vjn[lane];
+        acc = vk * sw_k + wk * sv_k;
+        acc2 = vk * wjn_k + wk * vjn_k;
       }
       acc = warp_sum(acc);
       acc2 = warp_sum(acc2);
@@ -695,10 +687,16 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
         P2[r + (long long)(S1_NB + i) * ldp] = v;
         Vh[r + (long long)j * ldv] = v;
       }
+      const double ajn_old = ajns[l];
+      __syncwarp();
+      if (lane == 1) {
+        ajs[l] = ajn_old;
+        ajns[l] = a_next;
+      }
     }
-    if (t < S1_NB) {
-      svp[t] = (t < i) ? sv[t] : 0.0;
-      swp[t] = (t < i) ? sw[t] : 0.0;
+    if (warp == 0) {
+      svp[((i + 1) & 1) * S1_NB + lane] = (lane < i) ? sv_k : 0.0;
+      swp[((i + 1) & 1) * S1_NB + lane] = (lane < i) ? sw_k : 0.0;
     }
     tau_p = tj;
     pending = true;
@@ -805,7 +803,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     const int64_t ldp = n;
     const bool one_barrier = env_i("TNAD_SYTRD_1B", 1) != 0;
     const int64_t NQ = (n + 3) / 4, NL = 4 * ((NQ + G - 1) / G);
-    const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 8 * S1_NB + 24) * sizeof(double);
+    const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 10 * S1_NB + 24) * sizeof(double);
     Tens upart, spart1, pub, redo, prof;
     double theta = 0.1;
     if (const char* ev = getenv("TNAD_SYTRD_THETA")) theta = atof(ev);
@@ -887,7 +885,7 @@ int64_t sytrd_vcols(int64_t n) { return (n + 127) / 128 * 128; }
 void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int64_t n, double* Z, int64_t ldz, int64_t ncols) {
   const int64_t nref = n >= 3 ? n - 2 : 0;
   if (nref == 0) return;
-  const int kb = env_i("TNAD_APPLYQ_NB", n >= 4096 ? 128 : 64) >= 128 ? 128 : 64;
+  const int kb = env_i("TNAD_APPLYQ_NB", 128) >= 128 ? 128 : 64;   // measured: 128 wins at n = 2048 (2.5 vs 3.4 ms) and 6400 (46 vs 66 ms)
   const int64_t npan = (nref + kb - 1) / kb;
   TNAD_REQUIRE(npan * kb <= sytrd_vcols(n), "apply_q: reflector store too narrow");
   TNAD_CUDA(cudaFuncSetAttribute(k_larft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kb * kb + kb) * sizeof(double))));
@@ -987,7 +985,7 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
 SvdResult svd_symmetric_auto(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* Q0) {
   const int mode = env_i("TNAD_SYMEIG", -1);
   const int64_t n = A.dim[0];
-  const bool dc = mode == 2 || (mode < 0 && n >= env_i("TNAD_DC_MIN", 256));
+  const bool dc = mode == 2 || (mode < 0 && n >= env_i("TNAD_DC_MIN", 96));
   return dc ? svd_symmetric_dc(c, A, sym_add_transpose) : svd_symmetric(c, A, sym_add_transpose, Q0);
 }
 

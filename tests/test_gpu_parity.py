@@ -462,3 +462,113 @@ def test_permute_and_svd_symmetrized_device_pointers(ctx):
     u = U.cpu().numpy().reshape((n, n), order="F"); v = V.cpu().numpy().reshape((n, n), order="F"); s = S.cpu().numpy()
     assert np.abs(u * s @ v.T - (a + a.T)).max() < 1e-12
     assert np.abs(s - np.linalg.svd(a + a.T, compute_uv=False)).max() < 1e-12
+
+
+# ---- direct symmetric eigensolver: tridiagonalisation (tridiag.cu) + divide and conquer (stedc.cu) -----------------
+def _tridiag(d, e):
+    return np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 65, 130, 257, 700])
+def test_stedc_random_vs_lapack(ctx, n):
+    rng = np.random.default_rng(n)
+    d, e = rng.standard_normal(n), rng.standard_normal(max(n - 1, 0))
+    lam, Z = ctx.stedc(d, e)
+    Tm = _tridiag(d, e) if n > 1 else np.array([[d[0]]])
+    ref = np.linalg.eigvalsh(Tm)
+    nrm = max(np.abs(ref).max(), 1e-300)
+    assert np.all(np.diff(lam) >= 0)
+    assert np.abs(lam - ref).max() <= 5e-14 * nrm
+    assert np.abs(Tm @ Z - Z * lam).max() <= 5e-14 * nrm
+    assert np.abs(Z.T @ Z - np.eye(n)).max() <= 5e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["graded", "clustered", "wilkinson", "zero_offdiag", "constant"])
+def test_stedc_hard_spectra(ctx, kind):
+    rng = np.random.default_rng(11)
+    n = 300
+    if kind == "graded":
+        d, e = 10.0 ** (-rng.uniform(0, 18, n)), 10.0 ** (-rng.uniform(0, 18, n - 1))
+    elif kind == "clustered":     # tridiagonal of a matrix with three huge eigenvalue clusters: deflation by Givens chains
+        import scipy.linalg as sl
+        q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        w = np.concatenate([np.ones(100), np.zeros(100), -np.ones(100)]) + 1e-14 * rng.standard_normal(n)
+        h = sl.hessenberg((q * w) @ q.T)
+        d, e = np.diag(h).copy(), np.diag(h, 1).copy()
+    elif kind == "wilkinson":
+        d, e = np.abs(np.arange(n) - n // 2).astype(float), np.ones(n - 1)
+    elif kind == "zero_offdiag":
+        d, e = rng.standard_normal(n), np.zeros(n - 1)
+    else:
+        d, e = np.full(n, 2.0), np.full(n - 1, -1.0)
+    lam, Z = ctx.stedc(d, e)
+    Tm = _tridiag(d, e)
+    ref = np.linalg.eigvalsh(Tm)
+    nrm = np.abs(ref).max()
+    assert np.abs(lam - ref).max() <= 1e-13 * nrm
+    assert np.abs(Tm @ Z - Z * lam).max() <= 1e-13 * nrm
+    assert np.abs(Z.T @ Z - np.eye(n)).max() <= 1e-13
+
+
+def _sym_cases(n, rng):
+    a = rng.standard_normal((n, n))
+    yield "random", a + a.T
+    b = rng.standard_normal((n, max(2, n // 10)))
+    yield "low_rank", b @ b.T
+    q, _ = np.linalg.qr(a)
+    m = (q * (10.0 ** (-np.arange(n) / 6.0) * rng.choice([-1.0, 1.0], n))) @ q.T
+    yield "decaying", m + m.T
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("one_barrier", ["1", "0"])
+@pytest.mark.parametrize("n", [3, 4, 10, 33, 97, 130, 259, 600])
+def test_sytrd_backward_error(ctx, n, one_barrier, monkeypatch):
+    """A = Q T Q' to machine precision for both panel kernels, including rank-deficient input (the cancellation
+    guard of the one-barrier kernel) and sizes that are odd / not multiples of the ownership quad."""
+    monkeypatch.setenv("TNAD_SYTRD_1B", one_barrier)
+    rng = np.random.default_rng(100 + n)
+    for name, a in _sym_cases(n, rng):
+        d, e, q = ctx.sytrd(a)
+        Tm = _tridiag(d, e)
+        nrm = np.linalg.norm(a, 2)
+        assert np.abs(q.T @ q - np.eye(n)).max() <= 2e-14, (name, n)
+        assert np.abs(q @ Tm @ q.T - a).max() <= 2e-14 * nrm, (name, n)
+        assert np.abs(np.linalg.eigvalsh(Tm) - np.linalg.eigvalsh(a)).max() <= 2e-14 * nrm, (name, n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("n", [64, 300, 520])
+def test_svd_sym_both_solvers(ctx, n, mode, monkeypatch):
+    """tnad_svd_sym through the block-Jacobi solver (1) and the tridiagonal divide-and-conquer solver (2)."""
+    monkeypatch.setenv("TNAD_SYMEIG", mode)
+    rng = np.random.default_rng(n)
+    for name, a in _sym_cases(n, rng):
+        u, s, v = ctx.svd_sym(a)
+        ref = np.linalg.svd(a, compute_uv=False)
+        assert np.all(np.diff(s) <= 0)
+        assert np.abs(s - ref).max() <= 1e-12 * ref[0], (name, mode)
+        assert np.abs((u * s) @ v.T - a).max() <= 1e-12 * ref[0], (name, mode)
+        assert np.abs(u.T @ u - np.eye(n)).max() <= 1e-12, (name, mode)
+        assert np.abs(np.abs(np.sum(u * v, axis=0)) - 1.0).max() <= 1e-12      # v = +-u column by column
+
+
+@pytest.mark.gpu
+def test_energy_gradient_same_with_both_solvers(ctx, monkeypatch):
+    """The headline path (energy + gradient) must not depend on which eigensolver ran (chi*D = 256 >= TNAD_DC_MIN)."""
+    rng = np.random.default_rng(5)
+    h = T.hamiltonian(T.Heisenberg())
+    A = T.indexperm_symmetrize(T.SquareIPEPS(rng.standard_normal((2, 2, 2, 2, 2)))).bulk
+    out = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("TNAD_SYMEIG", mode)
+        out[mode] = ctx.energy(h, A, 64, 0.0, 4, grad=True)
+    e1, g1 = out["1"]
+    e2, g2 = out["2"]
+    assert abs(e1 - e2) <= 1e-10 * abs(e1)
+    assert np.abs(g1 - g2).max() <= 1e-8 * np.abs(g1).max()
+    er, gr = O.energy_value_and_grad(h, A, 64, 0.0, 4)
+    assert abs(e2 - er) <= 1e-10 * abs(er) and np.abs(g2 - gr).max() <= 1e-8 * np.abs(gr).max()

@@ -300,3 +300,60 @@ def test_gloo_world2_sharded_ctmrgstep_schedule(tmp_path):
     rows = [json.load(open(tmp_path / f"r{k}.json")) for k in range(2)]
     assert [x["start"] for x in rows] == [0, 4] and all(x["width"] == 4 for x in rows)
     assert all(x["err"] < 1e-12 for x in rows), rows
+
+
+# ---- NumPy statements of the two eigensolver algorithms the kernels implement (tools/*_proto.py) ------------------------
+def _load_tool(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("kind", ["random", "graded", "wilkinson"])
+def test_divide_and_conquer_prototype(kind):
+    P = _load_tool("stedc_proto")
+    rng = np.random.default_rng(2)
+    n = 90
+    if kind == "random":
+        d, e = rng.standard_normal(n), rng.standard_normal(n - 1)
+    elif kind == "graded":
+        d, e = 10.0 ** (-rng.uniform(0, 16, n)), 10.0 ** (-rng.uniform(0, 16, n - 1))
+    else:
+        d, e = np.abs(np.arange(n) - n // 2).astype(float), np.ones(n - 1)
+    lam, Z = P.stedc(d, e, smax=8)
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    o = np.argsort(lam)
+    ref = np.linalg.eigvalsh(Tm)
+    nrm = np.abs(ref).max()
+    assert np.abs(lam[o] - ref).max() < 1e-13 * nrm
+    assert np.abs(Tm @ Z - Z * lam).max() < 1e-13 * nrm and np.abs(Z.T @ Z - np.eye(n)).max() < 1e-13
+    assert P.leaf_size(6400, 64) == (50, 7) and P.leaf_size(2048, 16) == (16, 7)
+
+
+@pytest.mark.parametrize("kind", ["random", "low_rank", "decaying"])
+def test_one_barrier_tridiagonalisation_prototype(kind):
+    P = _load_tool("sytrd1b_proto")
+    rng = np.random.default_rng(4)
+    n = 70
+    a = rng.standard_normal((n, n))
+    if kind == "random":
+        a = a + a.T
+    elif kind == "low_rank":
+        b = rng.standard_normal((n, 6))
+        a = b @ b.T
+    else:
+        q, _ = np.linalg.qr(a)
+        a = (q * 10.0 ** (-np.arange(n) / 4.0)) @ q.T
+        a = a + a.T
+    P.THETA = 0.1
+    P.REDO[0] = 0
+    d, e, Vh, tau = P.sytrd_one_barrier(a, nb=16)
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    Q = P.form_q(Vh, tau)
+    nrm = np.linalg.norm(a, 2)
+    assert np.abs(Q.T @ Q - np.eye(n)).max() < 1e-13
+    assert np.abs(Q @ Tm @ Q.T - a).max() < 1e-13 * nrm
+    if kind == "low_rank":
+        assert P.REDO[0] >= 1          # the cancellation guard must fire at the rank boundary
