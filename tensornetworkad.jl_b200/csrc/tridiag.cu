@@ -33,6 +33,25 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // All CTAs of a cooperative launch meet here: CTA b publishes `epoch` in its own flag line (release) and every CTA
 // polls all flags (one acquire load per thread) - no contended atomic, one L2 round trip after the last arrival.
+// Counter variant (A/B switch TNAD_SYTRD_BAR=1): one release-add per CTA on a single counter, thread 0 polls it.
+__device__ __forceinline__ void grid_barrier_ctr(unsigned int* ctr, unsigned int target, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+    const long long t0 = clock64();
+    unsigned int v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (clock64() - t0 > 6000000000LL) {
+        *err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned int* flags, unsigned int epoch, int G, int* err, int* s_to) {
   __syncthreads();
   if (threadIdx.x == 0) asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(flags + 32 * blockIdx.x), "r"(epoch) : "memory");
@@ -275,9 +294,11 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
                                                            double* P1, double* P2, long long ldp, double* Vh, long long ldv,
                                                            double* tau, double* dd, double* ee, double* upart, double* spart,
                                                            double* pub, unsigned int* flags, unsigned int epoch0, int* err,
-                                                           double theta, int* redo_count, long long* prof) {
+                                                           double theta, int* redo_count, long long* prof, int bar_mode,
+                                                           unsigned int ctr_base) {
   extern __shared__ double sm[];
   const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  unsigned int ctr_target = ctr_base;
   const int NQ = (n + 3) >> 2;                 // row quads
   const int NL = 4 * ((NQ + G - 1) / G);
   double* gs = sm;               // running column g (owned rows)
@@ -407,7 +428,12 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
       }
     }
     S1_PROF(1)
-    grid_barrier(flags, ++epoch, G, err, &s_to);
+    if (bar_mode) {
+      ctr_target += (unsigned int)G;
+      grid_barrier_ctr(flags + 32 * G, ctr_target, err);
+    } else {
+      grid_barrier(flags, ++epoch, G, err, &s_to);
+    }
     S1_PROF(2)
     // ---------------- post-barrier: gather.  All loads are issued from fully unrolled register arrays before the
     // first reduction, so the phase costs one L2 round trip (G <= 160). ----------------
@@ -819,11 +845,13 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     Tens P1 = t_alloc(c, {ldp, 2 * nb}, true), P2 = t_alloc(c, {ldp, 2 * nb}, true);
     const int64_t nchmax = (n + ST_CH - 1) / ST_CH;
     Tens ppart = t_alloc(c, {n, nchmax}), spart = t_alloc(c, {2 * nb, nchmax}), pvpart = t_alloc(c, {G});
-    Tens ctl = t_alloc(c, {16 * (int64_t)G + 2}, true);   // one 128-byte flag line per CTA, then the error flag
+    Tens ctl = t_alloc(c, {16 * (int64_t)G + 32}, true);   // one 128-byte flag line per CTA, the counter line, the error flag
     unsigned int* bar = reinterpret_cast<unsigned int*>(ctl.p);
-    int* err = reinterpret_cast<int*>(ctl.p + 16 * (int64_t)G);
+    int* err = reinterpret_cast<int*>(ctl.p + 16 * (int64_t)G + 16);
     unsigned int bar_base = 0;
     int dbg = env_i("TNAD_SYTRD_DBG", 0);
+    int bar_mode = env_i("TNAD_SYTRD_BAR", 1);   // 1: single release-add counter (measured 3.6k vs 4.4k cycles per barrier), 0: per-CTA flags
+    unsigned int ctr_base = 0;
     for (int64_t j0 = 0; j0 < nref; j0 += nb) {
       int nbc = (int)std::min<int64_t>(nb, nref - j0);
       int ni = (int)n, j0i = (int)j0, nbi = nb;
@@ -834,7 +862,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       double *upp = upart.p, *spp = spart1.p, *pubp = pub.p;
       int* redop = reinterpret_cast<int*>(redo.p);
       long long* profp = env_i("TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(prof.p) : nullptr;
-      void* args1[] = {&Ac, &lda_, &ni, &j0i, &nbc, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &upp, &spp, &pubp, &bar, &bar_base, &err, &theta, &redop, &profp};
+      void* args1[] = {&Ac, &lda_, &ni, &j0i, &nbc, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &upp, &spp, &pubp, &bar, &bar_base, &err, &theta, &redop, &profp, &bar_mode, &ctr_base};
       {
         KTimer kt(c, KF_EIG);
         if (one_barrier) TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel1, dim3(G), dim3(ST_NT), args1, smem1, st));
@@ -842,6 +870,9 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       }
       c->launches++;
       bar_base += (unsigned int)(2 * nbc + 2);   // barrier epochs this launch may consume
+      if (bar_mode) {   // the counter variant needs the exact number of barriers of the launch: reset the counter instead
+        TNAD_CUDA(cudaMemsetAsync(bar + 32 * G, 0, sizeof(unsigned int), st));
+      }
       // trailing update A22 -= [V W] [W V]'
       const int64_t jt = j0 + nbc, nt = n - jt;
       if (nt > 0) {
