@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
                                                            double* tau, double* dd, double* ee, double* upart, double* spart,
                                                            double* pub, unsigned int* flags, unsigned int epoch0, int* err,
                                                            double theta, int* redo_count, long long* prof, int bar_mode,
-                                                           unsigned int ctr_base) {
-  extern __shared__ double sm[];
+                                                           unsigned int ctr_base, int cache_cap) {
+  extern __shared__ __align__(16) double sm[];
   const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   unsigned int ctr_target = ctr_base;
   const int NQ = (n + 3) >> 2;                 // row quads
@@ -321,14 +321,43 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
   double* vjr = wjn + S1_NB;     // V[j, :]
   double* wjr = vjr + S1_NB;     // W[j, :]
   double* misc = wjr + S1_NB;    // 24
+  double* cache = misc + 24;     // panel-resident copy of this CTA's highest columns of the trailing matrix (TMA)
   __shared__ int s_to;
+  __shared__ __align__(8) unsigned long long mbar;
   double* gpub = pub;                   // [2][n]
   double* apub = pub + 2 * (long long)n;
   double* wpub = pub + 4 * (long long)n;
   unsigned int epoch = epoch0, xc = 0;
   const int NLb = s1_first(b, G, n);           // owned rows with r < n
   const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<unsigned long long>(A) & 15ull) == 0);
-  if (t == 0) s_to = 0;
+  // ---- panel-resident column cache: the trailing matrix is constant during the panel, so the columns this CTA
+  // multiplies in every matvec are staged ONCE per launch by bulk TMA copies (one elected thread, mbarrier with the
+  // expected byte count) and read from shared memory by all 32 columns of the panel.  What does not fit streams
+  // from L2 as before.
+  const int r_lo = 4 * ((j0 + 1) >> 2);
+  const int Lr = n - r_lo;
+  const int lc0 = s1_first(b, G, j0 + 1);
+  int ncache = (vec_ok && Lr > 0 && (Lr & 1) == 0) ? max(0, min(NLb - lc0, cache_cap / Lr)) : 0;
+  if (2 * ncache < NLb - lc0) ncache = 0;      // not worth it unless at least half of the owned columns fit
+  const int lcs = NLb - ncache;                 // local columns [lcs, NLb) are cached
+  const unsigned int mbar_s = (unsigned int)__cvta_generic_to_shared(&mbar);
+  if (t == 0) {
+    s_to = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0 && ncache > 0) {
+    const unsigned int bytes = (unsigned int)Lr * 8u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes * (unsigned int)ncache) : "memory");
+    for (int q = 0; q < ncache; ++q) {
+      const double* src = A + (long long)s1_row(b, G, lcs + q) * lda + r_lo;
+      const unsigned int dst = (unsigned int)__cvta_generic_to_shared(cache + (long long)q * Lr);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                   "r"(bytes), "r"(mbar_s)
+                   : "memory");
+    }
+  }
   for (int l = t; l < NL; l += ST_NT) {
     const int r = s1_row(b, G, l);
     gs[l] = (r > j0 && r < n) ? A[r + (long long)j0 * lda] : 0.0;
@@ -338,6 +367,14 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
   }
   for (int q = t; q < NL * S1_NB; q += ST_NT) Vs[q] = Ws[q] = 0.0;
   if (t < 2 * S1_NB) svp[t] = swp[t] = 0.0;
+  if (ncache > 0) {   // all threads: wait for the staged columns (phase 0 of the barrier)
+    unsigned int ok = 0;
+    while (!ok)
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(ok)
+                   : "r"(mbar_s), "r"(0u)
+                   : "memory");
+  }
   __syncthreads();
 
   int i = 0;
@@ -359,23 +396,71 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
     const int lminj = s1_first(b, G, j);        // ... with r >= j
     // ---------------- pre-barrier ----------------
     if (!fin) {
-      // matvec partial on row quads: u_b[4q..4q+3] = sum over owned columns c >= jn of A[4q.., c] g[c]
+      // matvec partial: u_b[r] = sum over owned columns c >= jn of A[r, c] g[c].  A warp takes 128 consecutive rows,
+      // lane L the row pairs (2L, 2L+1) and (64+2L, 64+2L+1): every load is a contiguous 512 bytes per warp
+      // (coalesced from L2, conflict-free from the shared-memory cache) and the two halves of every 32-byte exchange
+      // sector are written by neighbouring lanes.
       double* up = upart + (long long)par * NQ * G * 4;
-      for (int q = (jn >> 2) + t; q < NQ; q += ST_NT) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const int r0 = 4 * q;
-        if (vec_ok && r0 + 3 < n) {
+      if (vec_ok && ncache > 0) {
+        const int rbase = 4 * (jn >> 2);
+        for (int blk = warp; rbase + blk * 128 < n; blk += ST_NW) {
+          const int ra = rbase + blk * 128 + 2 * lane, rb = ra + 64;
+          const bool oka = ra < n, okb = rb < n;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          const int lend = min(NLb, lcs);
 #pragma unroll 8
-          for (int l = lmin; l < NLb; ++l) {
-            const double2* col = reinterpret_cast<const double2*>(A + (long long)s1_row(b, G, l) * lda + r0);
+          for (int l = lmin; l < lend; ++l) {       // streamed columns
+            const double* col = A + (long long)s1_row(b, G, l) * lda;
             const double gl = gs[l];
-            const double2 x0 = col[0], x1 = col[1];
-            a0 += x0.x * gl;
-            a1 += x0.y * gl;
-            a2 += x1.x * gl;
-            a3 += x1.y * gl;
+            if (oka) {
+              const double2 x = *reinterpret_cast<const double2*>(col + ra);
+              a0 += x.x * gl;
+              a1 += x.y * gl;
+            }
+            if (okb) {
+              const double2 x = *reinterpret_cast<const double2*>(col + rb);
+              a2 += x.x * gl;
+              a3 += x.y * gl;
+            }
           }
-        } else {
+#pragma unroll 8
+          for (int l = max(lmin, lcs); l < NLb; ++l) {   // cached columns
+            const double* col = cache + (long long)(l - lcs) * Lr - r_lo;
+            const double gl = gs[l];
+            if (oka) {
+              const double2 x = *reinterpret_cast<const double2*>(col + ra);
+              a0 += x.x * gl;
+              a1 += x.y * gl;
+            }
+            if (okb) {
+              const double2 x = *reinterpret_cast<const double2*>(col + rb);
+              a2 += x.x * gl;
+              a3 += x.y * gl;
+            }
+          }
+          if (oka) *reinterpret_cast<double2*>(up + ((long long)(ra >> 2) * G + b) * 4 + (ra & 3)) = make_double2(a0, a1);
+          if (okb) *reinterpret_cast<double2*>(up + ((long long)(rb >> 2) * G + b) * 4 + (rb & 3)) = make_double2(a2, a3);
+        }
+      } else {
+        for (int q = (jn >> 2) + t; q < NQ; q += ST_NT) {
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          const int r0 = 4 * q;
+          if (vec_ok && r0 + 3 < n) {      // streamed, one 32-byte row quad per thread
+#pragma unroll 8
+            for (int l = lmin; l < NLb; ++l) {
+              const double2* col = reinterpret_cast<const double2*>(A + (long long)s1_row(b, G, l) * lda + r0);
+              const double gl = gs[l];
+              const double2 x0 = col[0], x1 = col[1];
+              a0 += x0.x * gl;
+              a1 += x0.y * gl;
+              a2 += x1.x * gl;
+              a3 += x1.y * gl;
+            }
+            double2* dst = reinterpret_cast<double2*>(up + ((long long)q * G + b) * 4);
+            dst[0] = make_double2(a0, a1);
+            dst[1] = make_double2(a2, a3);
+            continue;
+          }
           for (int l = lmin; l < NLb; ++l) {
             const double* col = A + (long long)s1_row(b, G, l) * lda + r0;
             const double gl = gs[l];
@@ -384,10 +469,10 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
             if (r0 + 2 < n) a2 += col[2] * gl;
             if (r0 + 3 < n) a3 += col[3] * gl;
           }
+          double2* dst = reinterpret_cast<double2*>(up + ((long long)q * G + b) * 4);
+          dst[0] = make_double2(a0, a1);
+          dst[1] = make_double2(a2, a3);
         }
-        double2* dst = reinterpret_cast<double2*>(up + ((long long)q * G + b) * 4);
-        dst[0] = make_double2(a0, a1);
-        dst[1] = make_double2(a2, a3);
       }
       S1_PROF(0)
       for (int l = lminj + t; l < NLb; l += ST_NT) {
@@ -831,11 +916,15 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     const int64_t NQ = (n + 3) / 4, NL = 4 * ((NQ + G - 1) / G);
     const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 10 * S1_NB + 24) * sizeof(double);
     Tens upart, spart1, pub, redo, prof;
+    size_t smem_total = 0;
+    int cache_cap = 0;
     double theta = 0.1;
     if (const char* ev = getenv("TNAD_SYTRD_THETA")) theta = atof(ev);
     if (one_barrier) {
       TNAD_REQUIRE(smem1 <= 200 * 1024, "sytrd: matrix too large");
-      TNAD_CUDA(cudaFuncSetAttribute(k_sytrd_panel1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      smem_total = env_i("TNAD_SYTRD_CACHE", 1) ? (size_t)(232448 - 256) : smem1;   // everything left of the 227 KB goes to the column cache
+      cache_cap = (int)((smem_total - smem1) / sizeof(double)) & ~1;
+      TNAD_CUDA(cudaFuncSetAttribute(k_sytrd_panel1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
       upart = t_alloc(c, {4 * NQ, (int64_t)G, 2});
       spart1 = t_alloc(c, {S1_SS, (int64_t)G, 2}, true);
       pub = t_alloc(c, {n, 6}, true);
@@ -862,10 +951,10 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       double *upp = upart.p, *spp = spart1.p, *pubp = pub.p;
       int* redop = reinterpret_cast<int*>(redo.p);
       long long* profp = env_i("TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(prof.p) : nullptr;
-      void* args1[] = {&Ac, &lda_, &ni, &j0i, &nbc, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &upp, &spp, &pubp, &bar, &bar_base, &err, &theta, &redop, &profp, &bar_mode, &ctr_base};
+      void* args1[] = {&Ac, &lda_, &ni, &j0i, &nbc, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &upp, &spp, &pubp, &bar, &bar_base, &err, &theta, &redop, &profp, &bar_mode, &ctr_base, &cache_cap};
       {
         KTimer kt(c, KF_EIG);
-        if (one_barrier) TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel1, dim3(G), dim3(ST_NT), args1, smem1, st));
+        if (one_barrier) TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel1, dim3(G), dim3(ST_NT), args1, smem_total, st));
         else TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(G), dim3(ST_NT), args, smem, st));
       }
       c->launches++;
