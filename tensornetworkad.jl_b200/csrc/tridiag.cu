@@ -917,13 +917,13 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 10 * S1_NB + 24) * sizeof(double);
     Tens upart, spart1, pub, redo, prof;
     size_t smem_total = 0;
-    int cache_cap = 0;
+    int cache_cap_max = 0;
     double theta = 0.1;
     if (const char* ev = getenv("TNAD_SYTRD_THETA")) theta = atof(ev);
     if (one_barrier) {
       TNAD_REQUIRE(smem1 <= 200 * 1024, "sytrd: matrix too large");
       smem_total = env_i("TNAD_SYTRD_CACHE", 1) ? (size_t)(232448 - 256) : smem1;   // everything left of the 227 KB goes to the column cache
-      cache_cap = (int)((smem_total - smem1) / sizeof(double)) & ~1;
+      cache_cap_max = (int)((smem_total - smem1) / sizeof(double)) & ~1;
       TNAD_CUDA(cudaFuncSetAttribute(k_sytrd_panel1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
       upart = t_alloc(c, {4 * NQ, (int64_t)G, 2});
       spart1 = t_alloc(c, {S1_SS, (int64_t)G, 2}, true);
@@ -948,13 +948,19 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       double *P1p = P1.p, *P2p = P2.p, *pp = ppart.p, *sp = spart.p, *pvp = pvpart.p;
       void* args[] = {&A, &lda_, &ni, &j0i, &nbc, &nbi, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &pp, &sp, &pvp, &bar, &bar_base, &err, &dbg};
       const double* Ac = A;
+      // the column cache takes the whole shared memory (and with it most of L1): only worth it when at least half of
+      // a CTA's columns fit, otherwise launch with the small footprint and stream (measured at n = 6400: 231 vs 259 ms)
+      const int64_t Lr_p = n - 4 * ((j0 + 1) / 4), ncol_p = 4 * (((n - j0 + 3) / 4 + G - 1) / G);
+      const bool use_cache = cache_cap_max > 0 && Lr_p > 0 && 2 * (cache_cap_max / Lr_p) >= ncol_p;
+      int cache_cap = use_cache ? cache_cap_max : 0;
+      const size_t smem_launch = use_cache ? smem_total : smem1;
       double *upp = upart.p, *spp = spart1.p, *pubp = pub.p;
       int* redop = reinterpret_cast<int*>(redo.p);
       long long* profp = env_i("TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(prof.p) : nullptr;
       void* args1[] = {&Ac, &lda_, &ni, &j0i, &nbc, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &upp, &spp, &pubp, &bar, &bar_base, &err, &theta, &redop, &profp, &bar_mode, &ctr_base, &cache_cap};
       {
         KTimer kt(c, KF_EIG);
-        if (one_barrier) TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel1, dim3(G), dim3(ST_NT), args1, smem_total, st));
+        if (one_barrier) TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel1, dim3(G), dim3(ST_NT), args1, smem_launch, st));
         else TNAD_CUDA(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(G), dim3(ST_NT), args, smem, st));
       }
       c->launches++;
