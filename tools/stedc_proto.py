@@ -3,7 +3,7 @@ same stages, same data layout, used to settle the numerics before writing the ke
 not the parity oracle).
 
 Stages per merge (Cuppen / Gu-Eisenstat, cf. LAPACK dlaed1-4 published algorithm):
-  z, rho  -> sort d -> deflate (tiny z; close d via Givens chain) -> secular roots by bit-pattern bisection in the
+  z, rho  -> sort d -> deflate (tiny z; close d via Givens chain) -> secular roots by safeguarded regula falsi in the
   variable shifted to the nearest pole -> z-hat (Loewner) -> eigenvectors -> S (m x m) -> Q_new = Q S
 """
 import numpy as np
@@ -30,6 +30,67 @@ def bisect_bits(fun, hi):
         else:
             lo_b = mid_b
     return np.int64(hi_b).view(np.float64)
+
+
+EVALS = [0, 0]     # [function evaluations, roots]
+
+
+def secular_root(dn, z2, rho, j):
+    """Root j of 1 + rho sum z_i^2/(d_i - lam) in the variable x = |lam - d_org| shifted to the nearest pole:
+    safeguarded regula falsi (Illinois) on phi(x) = F(x) x (Delta - x)/Delta (both neighbouring poles divided out),
+    stopped by the dlaed4 criterion |F| <= 4 eps (1 + rho sum |terms|).  Returns (org, mu, d - d_org)."""
+    k = dn.size
+    if j < k - 1:
+        gap = dn[j + 1] - dn[j]
+        mid = 0.5 * gap
+        fmid = 1.0 + rho * np.sum(z2 / ((dn - dn[j]) - mid))
+        org, sgn = (j, 1.0) if fmid >= 0 else (j + 1, -1.0)
+        hi, Dlt = mid, gap
+    else:
+        org, sgn, hi, Dlt = j, 1.0, rho * np.sum(z2) * (1 + 8 * EPS) + 1e-300, None
+    delta = dn - dn[org]
+    mask = np.ones(k, bool)
+    mask[org] = False
+    zo = z2[org]
+
+    def ev(x):
+        t = z2[mask] / (delta[mask] - sgn * x)
+        Fx = (x + rho * x * np.sum(t) - rho * zo) if sgn > 0 else -(x + rho * x * np.sum(t) + rho * zo)
+        S = 1.0 + rho * (np.sum(np.abs(t)) + zo / x)
+        EVALS[0] += 1
+        return Fx, S
+
+    w = (lambda x: (Dlt - x) / Dlt) if Dlt is not None else (lambda x: 1.0)
+    xa, fa, xb = 0.0, -rho * zo, hi
+    Fb, _ = ev(xb)
+    fb = Fb * w(xb)
+    xc = xb
+    EVALS[1] += 1
+    if fb > 0:
+        side = 0
+        for _ in range(100):
+            den = fb - fa
+            xc = (xa * fb - xb * fa) / den if den != 0 else 0.5 * (xa + xb)
+            if not (xa < xc < xb):
+                xc = 0.5 * (xa + xb)
+            if not (xa < xc < xb):
+                xc = xb
+                break
+            Fc, Sc = ev(xc)
+            if abs(Fc) <= 4 * EPS * Sc * xc:
+                break
+            fc = Fc * w(xc)
+            if fc < 0:
+                xa, fa = xc, fc
+                if side == -1:
+                    fb *= 0.5
+                side = -1
+            else:
+                xb, fb = xc, fc
+                if side == 1:
+                    fa *= 0.5
+                side = 1
+    return org, sgn * xc, delta
 
 
 def merge(d, Q, z, rho):
@@ -76,22 +137,7 @@ def merge(d, Q, z, rho):
     Delta = np.empty((k, k))          # Delta[i, j] = dn[i] - lam[j]
     z2 = zn * zn
     for j in range(k):
-        if j < k - 1:
-            gap = dn[j + 1] - dn[j]
-            mid = 0.5 * gap
-            dl = dn - dn[j]
-            fmid = 1.0 + rho * np.sum(z2 / (dl - mid))
-            if fmid >= 0:          # root in the left half: origin dn[j], mu in (0, gap/2]
-                org, delta = j, dl
-                mu = bisect_bits(lambda x: 1.0 + rho * np.sum(z2 / (delta - x)), mid)
-            else:                  # origin dn[j+1], mu = -nu, nu in (0, gap/2)
-                org, delta = j + 1, dn - dn[j + 1]
-                nu = bisect_bits(lambda x: -(1.0 + rho * np.sum(z2 / (delta + x))), mid)
-                mu = -nu
-        else:
-            org, delta = j, dn - dn[j]
-            hi = rho * np.sum(z2)
-            mu = bisect_bits(lambda x: 1.0 + rho * np.sum(z2 / (delta - x)), hi * (1 + 4 * EPS) + np.finfo(float).tiny)
+        org, mu, delta = secular_root(dn, z2, rho, j)
         lam[j] = dn[org] + mu
         Delta[:, j] = delta - mu
     # Loewner: zhat_i^2 = prod_j (lam_j - d_i) / (rho prod_{j != i} (d_j - d_i))
