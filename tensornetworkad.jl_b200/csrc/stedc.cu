@@ -49,9 +49,12 @@ __global__ void k_dc_setup(const double* __restrict__ dd, const double* __restri
                            double* dp, double* ep, double* beta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  double d = i < n ? dd[i] : scale * (4.0 + (double)(i - n) / (double)N);
-  const double el = (i > 0 && i - 1 < n - 1) ? ee[i - 1] : 0.0;   // coupling (i-1, i)
-  const double er = (i < n - 1) ? ee[i] : 0.0;                    // coupling (i, i+1)
+  // the problem is scaled to max(|d|, |e|) = 1 (LAPACK dstedc does the same with dlascl): the deflation tolerances
+  // compare against the O(1) entries of z
+  const double rs = 1.0 / scale;
+  double d = i < n ? dd[i] * rs : (4.0 + (double)(i - n) / (double)N);
+  const double el = (i > 0 && i - 1 < n - 1) ? ee[i - 1] * rs : 0.0;   // coupling (i-1, i)
+  const double er = (i < n - 1) ? ee[i] * rs : 0.0;                    // coupling (i, i+1)
   double b = 0.0, e_out = er;
   if (i % s == 0 && i > 0) {
     b = el;
@@ -64,6 +67,11 @@ __global__ void k_dc_setup(const double* __restrict__ dd, const double* __restri
   dp[i] = d;
   ep[i] = e_out;
   beta[i] = b;
+}
+
+__global__ void k_scale_vec(double* x, int n, double f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= f;
 }
 
 __global__ void k_absmax2(const double* __restrict__ a, int na, const double* __restrict__ b, int nbv, double* out) {
@@ -681,6 +689,9 @@ void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam
     lam = lamA;
     Z = Qa;
   }
+  k_scale_vec<<<(int)((N + 255) / 256), 256, 0, st>>>(lam.p, (int)N, scale);
+  c->launches++;
+  TNAD_CUDA(cudaGetLastError());
 }
 
 }  // namespace tnad

@@ -513,12 +513,14 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
       }
     }
     S1_PROF(1)
+    const long long tw0 = (prof && t == 0) ? clock64() : 0;
     if (bar_mode) {
       ctr_target += (unsigned int)G;
       grid_barrier_ctr(flags + 32 * G, ctr_target, err);
     } else {
       grid_barrier(flags, ++epoch, G, err, &s_to);
     }
+    if (prof && t == 0) prof[8 + b] += clock64() - tw0;   // per-CTA time inside the barrier (straggler analysis)
     S1_PROF(2)
     // ---------------- post-barrier: gather.  All loads are issued from fully unrolled register arrays before the
     // first reduction, so the phase costs one L2 round trip (G <= 160). ----------------
@@ -929,7 +931,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       spart1 = t_alloc(c, {S1_SS, (int64_t)G, 2}, true);
       pub = t_alloc(c, {n, 6}, true);
       redo = t_alloc(c, {2}, true);
-      prof = t_alloc(c, {8}, true);
+      prof = t_alloc(c, {8 + (int64_t)G}, true);
     }
     Tens P1 = t_alloc(c, {ldp, 2 * nb}, true), P2 = t_alloc(c, {ldp, 2 * nb}, true);
     const int64_t nchmax = (n + ST_CH - 1) / ST_CH;
@@ -990,8 +992,16 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       int rc = 0;
       TNAD_CUDA(cudaMemcpy(&rc, redo.p, sizeof(int), cudaMemcpyDeviceToHost));
       fprintf(stderr, "[tnad dc] sytrd: %d of %lld columns redone (cancellation guard, theta %.3g)\n", rc, (long long)nref, theta);
-      long long ph[8];
-      TNAD_CUDA(cudaMemcpy(ph, prof.p, sizeof(ph), cudaMemcpyDeviceToHost));
+      std::vector<long long> ph((size_t)8 + G);
+      TNAD_CUDA(cudaMemcpy(ph.data(), prof.p, ph.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      {
+        std::vector<std::pair<long long, int>> w;
+        for (int q = 0; q < G; ++q) w.push_back({ph[(size_t)8 + q], q});
+        std::sort(w.begin(), w.end());
+        fprintf(stderr, "[tnad dc] sytrd barrier wait per CTA (cycles/column): min %.0f (cta %d), %.0f (cta %d), %.0f (cta %d) ... median %.0f ... max %.0f (cta %d)\n",
+                (double)w[0].first / nref, w[0].second, (double)w[1].first / nref, w[1].second, (double)w[2].first / nref, w[2].second,
+                (double)w[(size_t)G / 2].first / nref, (double)w[(size_t)G - 1].first / nref, w[(size_t)G - 1].second);
+      }
       fprintf(stderr, "[tnad dc] sytrd CTA0 cycles/column: matvec %.0f  sums+publish %.0f  barrier %.0f  gather %.0f  scalars %.0f  warp0 %.0f  rows %.0f\n",
               (double)ph[0] / nref, (double)ph[1] / nref, (double)ph[2] / nref, (double)ph[3] / nref, (double)ph[4] / nref,
               (double)ph[5] / nref, (double)ph[6] / nref);
@@ -1048,6 +1058,15 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
   k_load_symm<<<nbk, 256, 0, st>>>(Aw.p, n, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
+  // scale to max|a_ij| = 1 (the reflector norms are plain sums of squares; LAPACK rescales inside dlarfg instead)
+  double amax = 0.0;
+  {
+    Tens sc = t_alloc(c, {2});
+    reduce(c, RED_ABSMAX, Aw, nullptr, sc.p);
+    d2h(c, &amax, sc.p, 1);
+    if (amax > 0.0 && std::isfinite(amax)) scale_dev(c, Aw, Aw, sc.p, SC_INV);
+    else amax = 1.0;
+  }
   Tens Vh = t_alloc(c, {n, sytrd_vcols(n)}, true), tau = t_alloc(c, {sytrd_vcols(n)}, true), dd = t_alloc(c, {n}), ee = t_alloc(c, {n}, true);
   const bool debug = env_i("TNAD_DC_DEBUG", 0) != 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1073,6 +1092,7 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
   }
   std::vector<double> lh((size_t)N);
   d2h(c, lh.data(), lam.p, (size_t)N);
+  for (auto& v : lh) v *= amax;
   // the N - n pad eigenvalues are the largest ones (stedc puts them above 3 |T|)
   std::vector<int> idx((size_t)N);
   for (int64_t i = 0; i < N; ++i) idx[(size_t)i] = (int)i;

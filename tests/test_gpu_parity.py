@@ -572,3 +572,42 @@ def test_energy_gradient_same_with_both_solvers(ctx, monkeypatch):
     assert np.abs(g1 - g2).max() <= 1e-8 * np.abs(g1).max()
     er, gr = O.energy_value_and_grad(h, A, 64, 0.0, 4)
     assert abs(e2 - er) <= 1e-10 * abs(er) and np.abs(g2 - gr).max() <= 1e-8 * np.abs(gr).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["zero", "identity", "diag_repeated", "tiny_scale", "denormal_squares", "huge_scale", "rank_one", "block_diag"])
+def test_svd_sym_direct_solver_degenerate_inputs(ctx, kind, monkeypatch):
+    """Inputs on which every reflector / merge degenerates (tau = 0, rho = 0, full deflation)."""
+    monkeypatch.setenv("TNAD_SYMEIG", "2")
+    rng = np.random.default_rng(9)
+    n = 150
+    if kind == "zero":
+        a = np.zeros((n, n))
+    elif kind == "identity":
+        a = np.eye(n)
+    elif kind == "diag_repeated":
+        a = np.diag(np.repeat([3.0, -1.0, 0.5], n // 3))
+    elif kind == "tiny_scale":
+        b = rng.standard_normal((n, n))
+        a = 1e-120 * (b + b.T)
+    elif kind == "denormal_squares":      # squares of the entries underflow
+        b = rng.standard_normal((n, n))
+        a = 1e-200 * (b + b.T)
+    elif kind == "huge_scale":            # squares of the entries overflow
+        b = rng.standard_normal((n, n))
+        a = 1e200 * (b + b.T)
+    elif kind == "rank_one":
+        v = rng.standard_normal(n)
+        a = np.outer(v, v)
+    else:
+        a = np.zeros((n, n))
+        b = rng.standard_normal((50, 50))
+        a[:50, :50] = b + b.T
+        a[100:, 100:] = np.eye(50) * 2.0
+    u, s, v = ctx.svd_sym(a)
+    ref = np.linalg.svd(a, compute_uv=False)
+    scale = max(ref[0], 1e-300)
+    assert np.all(np.isfinite(u)) and np.all(np.isfinite(s)) and np.all(np.isfinite(v))
+    assert np.abs(s - ref).max() <= 1e-12 * scale
+    assert np.abs((u * s) @ v.T - a).max() <= 1e-12 * scale
+    assert np.abs(u.T @ u - np.eye(n)).max() <= 1e-12
