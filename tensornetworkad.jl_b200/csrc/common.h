@@ -231,6 +231,7 @@ struct SvdResult {
   double null_thr = 0.0;   // singular values <= null_thr are numerically null (their U columns are a completion)
   int sweeps = 0;
   int64_t rank_left = -1;   // >= 0: only the first rank_left columns of U are valid (null columns left zero)
+  int64_t rank_right = -1;  // >= 0: the same for V (Jordan-Wielandt route; the Jacobi route always returns the full V)
 };
 // A: any rank-2 strided view (m x n). If sym_add_transpose, the matrix decomposed is A + A^T (m == n).
 // V0 (optional, n x n orthogonal): warm start for square inputs.

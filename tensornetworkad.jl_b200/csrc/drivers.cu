@@ -14,13 +14,16 @@ namespace tnad {
 // svd_back
 // =====================================================================================================
 Tens svd_back_dev(tnad_ctx* c, const Tens& U, const Tens& S, const Tens& V, const Tens* dUk, const Tens* dS,
-                  const Tens* dVk, int64_t k, double eta, int64_t r_valid) {
+                  const Tens* dVk, int64_t k, double eta, int64_t r_valid, int64_t r_valid_v) {
   Span sp(c, 4);
   const int64_t m = U.dim[0], n = V.dim[0], kk = S.dim[0];
   TNAD_REQUIRE(U.dim[1] == kk && V.dim[1] == kk && k <= kk, "svd_back: shape mismatch");
   // r_valid < kk: the columns r_valid.. of U (exactly-zero singular values) were not computed; their only
   // contribution, sum_i U_i U_i' dU_j / S_j, is applied as the projector (I - U_r U_r') instead.
   const bool proj = r_valid >= 0 && r_valid < kk && dUk != nullptr;
+  // the same for V (Jordan-Wielandt route): its null columns are zero, so V V' = V_r V_r' and the block
+  // "U Sinv (dV' - dV'V V')" below applies the whole complement of span(V_r) - null triplets included - exactly once
+  const bool projv = r_valid_v >= 0 && r_valid_v < kk && dVk != nullptr;
   const int64_t ru = proj ? r_valid : kk;
   Tens Ur = t_slice_last(U, 0, ru);
   Tens G1, G2;
@@ -61,13 +64,13 @@ Tens svd_back_dev(tnad_ctx* c, const Tens& U, const Tens& S, const Tens& V, cons
     T2 = contract_new(c, "mi,ij->mj", U, Rcol);
   }
   contract(c, "mj,nj->mn", T2, Vk, dA, 1.0, 1.0);
-  if (dUk && m != kk) {   // (dU - U U'dU) Sinv V'   (trg.jl:97-99)
+  if (dUk && m != kk && !proj) {   // (dU - U U'dU) Sinv V'   (trg.jl:97-99); the projector path above already covers it
     Tens P = t_clone(c, *dUk);
     contract(c, "mi,ij->mj", U, G1, P, -1.0, 1.0);
     colscale_sinv(c, P.p, m, m, k, S.p, eta);
     contract(c, "mj,nj->mn", P, Vk, dA, 1.0, 1.0);
   }
-  if (dVk && n != kk) {   // U Sinv (dV' - dV'V V')   (trg.jl:101-103)
+  if (dVk && (n != kk || projv)) {   // U Sinv (dV' - dV'V V')   (trg.jl:101-103)
     Tens Q = t_clone(c, *dVk);
     contract(c, "ni,ij->nj", V, G2, Q, -1.0, 1.0);
     colscale_sinv(c, Q.p, n, n, k, S.p, eta);
@@ -95,7 +98,12 @@ TrgSplit trg_split(tnad_ctx* c, const Tens& t4, int64_t dmax, double tol) {
   TrgSplit sp;
   {
     Span s(c, 1);
-    sp.svd = svd_jacobi(c, t4, false, nullptr, /*complete_null=*/false);
+    // from order m + n >= 96 on: Jordan-Wielandt embedding + the direct symmetric eigensolver (TNAD_TRG_SVD=jacobi
+    // forces the one-sided block Jacobi path)
+    const int64_t mm = t4.dim[0] * t4.dim[1], nn = t4.dim[2] * t4.dim[3];
+    const char* ev = getenv("TNAD_TRG_SVD");
+    const bool jac = (ev && ev[0] == 'j') || mm + nn < 96;
+    sp.svd = jac ? svd_jacobi(c, t4, false, nullptr, /*complete_null=*/false) : svd_general_dc(c, t4);
   }
   const int64_t m = t4.dim[0] * t4.dim[1], n = t4.dim[2] * t4.dim[3];
   sp.k = trg_rank_rule(sp.svd.s_host, dmax, tol);
@@ -178,7 +186,7 @@ static Tens trg_split_back(tnad_ctx* c, const TrgSplit& sp, const Tens& du /*(d1
   const int64_t m = sp.svd.U.dim[0], n = sp.svd.V.dim[0], k = sp.k;
   Tens dUk = t_alloc(c, {m, k}), dVk = t_alloc(c, {n, k}), dS = t_alloc(c, {k});
   trg_factor_back(c, m, n, k, sp.svd.U.p, m, sp.svd.V.p, n, sp.svd.S.p, du.p, dvt.p, dUk.p, dVk.p, dS.p);
-  return svd_back_dev(c, sp.svd.U, sp.svd.S, sp.svd.V, &dUk, &dS, &dVk, k, eta, sp.svd.rank_left);
+  return svd_back_dev(c, sp.svd.U, sp.svd.S, sp.svd.V, &dUk, &dS, &dVk, k, eta, sp.svd.rank_left, sp.svd.rank_right);
 }
 
 Tens trg_backward(tnad_ctx* c, TrgTape& tape, double dlnZ) {

@@ -8,7 +8,7 @@ namespace tnad {
 // svd_back (trg.jl:72-105) for cotangents that live in the first k columns of U / V.
 // U: m x kk, S: kk, V: n x kk (kk = min(m,n)); dUk: m x k, dS: k, dVk: n x k (any may be null).
 Tens svd_back_dev(tnad_ctx* c, const Tens& U, const Tens& S, const Tens& V, const Tens* dUk, const Tens* dS,
-                  const Tens* dVk, int64_t k, double eta, int64_t r_valid = -1);
+                  const Tens* dVk, int64_t k, double eta, int64_t r_valid = -1, int64_t r_valid_v = -1);
 
 // ---- TRG ------------------------------------------------------------------------------------------
 struct TrgSplit {

@@ -14,6 +14,9 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
 // back unsorted, the pad eigenvalues being the N - n largest, their eigenvectors unit vectors in the pad rows.
 void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam, Tens& Z, int64_t& N);
 SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose);
+// general (rank-2 or rank-4 [(d1,d2),(d3,d4)] view) matrix through the Jordan-Wielandt embedding; only the r non-null
+// triplets are formed (rank_left = rank_right = r)
+SvdResult svd_general_dc(tnad_ctx* c, const Tens& A);
 // Solver selection for symmetric inputs: TNAD_SYMEIG = 1 block Jacobi (symeig.cu), 2 tridiagonal divide and conquer;
 // default: divide and conquer from n >= TNAD_DC_MIN (96) on (measured crossover: equal at n = 64, 1.5x faster at 96).
 SvdResult svd_symmetric_auto(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* Q0 = nullptr);

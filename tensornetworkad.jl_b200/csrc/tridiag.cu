@@ -883,6 +883,29 @@ __global__ void k_gather_cols(const double* __restrict__ Q, long long ldq, const
   }
 }
 
+// H[0:m, m:m+n] = A, H[m:, 0:m] = A' for the (d1,d2) x (d3,d4) strided view A (H zero-initialised, ld = ldh)
+__global__ void k_load_jw(double* H, long long ldh, const double* __restrict__ A, long long d1, long long d2, long long d3,
+                          long long d4, long long s1, long long s2, long long s3, long long s4) {
+  const long long m = d1 * d2, n = d3 * d4, total = m * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx % m, j = idx / m;
+    const double v = A[(i % d1) * s1 + (i / d1) * s2 + (j % d3) * s3 + (j / d3) * s4];
+    H[i + (m + j) * ldh] = v;
+    H[(m + j) + i * ldh] = v;
+  }
+}
+
+// U[:, q] = sqrt(2) Z[0:m, pos[q]], V[:, q] = sqrt(2) Z[m:m+n, pos[q]]
+__global__ void k_gather_jw(const double* __restrict__ Z, long long ldz, const int* __restrict__ pos, long long m, long long n,
+                            double* __restrict__ U, double* __restrict__ V) {
+  const long long q = blockIdx.x;
+  const double* src = Z + (long long)pos[q] * ldz;
+  const double r2 = 1.4142135623730951;
+  for (long long i = threadIdx.x; i < m; i += blockDim.x) U[i + q * m] = r2 * src[i];
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) V[i + q * n] = r2 * src[m + i];
+}
+
 int env_i(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -1049,15 +1072,10 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
 }
 
 // Eigen-decomposition route: tridiagonalise, divide and conquer, back-transform.
-SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
-  TNAD_REQUIRE(A.rank == 2 && A.dim[0] == A.dim[1], "svd_symmetric_dc: need a square matrix");
-  const int64_t n = A.dim[0];
+// Eigen-decomposition of the symmetric matrix in Aw (n x n contiguous, overwritten): eigenvalues to the host (lh, N
+// entries incl. the pads, already rescaled), eigenvectors as columns of Z (N x N, leading dimension N; rows >= n are pad rows).
+static void eigh_dc(tnad_ctx* c, Tens& Aw, int64_t n, std::vector<double>& lh, Tens& Z, int64_t& N) {
   cudaStream_t st = c->stream;
-  Tens Aw = t_alloc(c, {n, n});
-  const int nbk = (int)std::max<long long>(1, std::min<long long>((n * n + 1023) / 1024, 148 * 8));
-  k_load_symm<<<nbk, 256, 0, st>>>(Aw.p, n, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
-  c->launches++;
-  TNAD_CUDA(cudaGetLastError());
   // scale to max|a_ij| = 1 (the reflector norms are plain sums of squares; LAPACK rescales inside dlarfg instead)
   double amax = 0.0;
   {
@@ -1075,8 +1093,7 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
   if (debug) TNAD_CUDA(cudaEventRecord(ev[0], st));
   sytrd(c, Aw.p, n, n, Vh.p, n, tau.p, dd.p, ee.p);
   if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
-  Tens lam, Z;
-  int64_t N = 0;
+  Tens lam;
   stedc(c, dd.p, ee.p, n, lam, Z, N);   // Z: N x N (ld N), lam: N, pads carry eigenvalues above the spectrum
   if (debug) TNAD_CUDA(cudaEventRecord(ev[2], st));
   apply_q(c, Vh.p, n, tau.p, n, Z.p, N, N);
@@ -1090,9 +1107,25 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
     fprintf(stderr, "[tnad dc] n=%lld N=%lld sytrd %.2f ms  stedc %.2f ms  apply_q %.2f ms\n", (long long)n, (long long)N, a, b, d3);
     for (auto& e : ev) c->event_pool.push_back(e);
   }
-  std::vector<double> lh((size_t)N);
+  lh.resize((size_t)N);
   d2h(c, lh.data(), lam.p, (size_t)N);
   for (auto& v : lh) v *= amax;
+}
+
+// Eigen-decomposition route: tridiagonalise, divide and conquer, back-transform.
+SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
+  TNAD_REQUIRE(A.rank == 2 && A.dim[0] == A.dim[1], "svd_symmetric_dc: need a square matrix");
+  const int64_t n = A.dim[0];
+  cudaStream_t st = c->stream;
+  Tens Aw = t_alloc(c, {n, n});
+  const int nbk = (int)std::max<long long>(1, std::min<long long>((n * n + 1023) / 1024, 148 * 8));
+  k_load_symm<<<nbk, 256, 0, st>>>(Aw.p, n, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
+  c->launches++;
+  TNAD_CUDA(cudaGetLastError());
+  std::vector<double> lh;
+  Tens Z;
+  int64_t N = 0;
+  eigh_dc(c, Aw, n, lh, Z, N);
   // the N - n pad eigenvalues are the largest ones (stedc puts them above 3 |T|)
   std::vector<int> idx((size_t)N);
   for (int64_t i = 0; i < N; ++i) idx[(size_t)i] = (int)i;
@@ -1124,6 +1157,71 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
   sync(c);
   res.s_host = sval;
   res.null_thr = 16.0 * 2.220446049250313e-16 * std::sqrt(fro2);   // same absolute level as the Jacobi solver
+  res.sweeps = 0;
+  return res;
+}
+
+// General m x n matrix through the Jordan-Wielandt embedding H = [0 A; A' 0] (order m + n): the eigenpairs of H are
+// (+-sigma_i, [u_i; +-v_i]/sqrt(2)), so the positive eigenvalues above the noise level give (U_r, S_r, V_r) with the
+// absolute accuracy eps |A| of a LAPACK SVD.  The null triplets are NOT formed (the eigenvectors of the 2(n - r)-fold
+// zero eigenvalue mix left and right null vectors): rank_left = rank_right = r tells svd_back to apply their
+// contribution through the projectors I - U_r U_r', I - V_r V_r' (DESIGN.md 4.3).
+SvdResult svd_general_dc(tnad_ctx* c, const Tens& A4) {
+  // A4: rank-2 (m x n) or rank-4 [(d1,d2),(d3,d4)] strided view
+  TNAD_REQUIRE(A4.rank == 2 || A4.rank == 4, "svd_general_dc: need a rank-2 or rank-4 view");
+  Tens v = A4;
+  if (v.rank == 2) {
+    v.rank = 4;
+    v.dim[3] = 1; v.str[3] = 0;
+    v.dim[2] = A4.dim[1]; v.str[2] = A4.str[1];
+    v.dim[1] = 1; v.str[1] = 0;
+  }
+  const int64_t m = v.dim[0] * v.dim[1], n = v.dim[2] * v.dim[3], nh = m + n, kk = std::min(m, n);
+  cudaStream_t st = c->stream;
+  Tens H = t_alloc(c, {nh, nh}, true);
+  {
+    const long long total = m * n;
+    const int nbk = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148 * 16));
+    k_load_jw<<<nbk, 256, 0, st>>>(H.p, nh, v.p, v.dim[0], v.dim[1], v.dim[2], v.dim[3], v.str[0], v.str[1], v.str[2], v.str[3]);
+    c->launches++;
+    TNAD_CUDA(cudaGetLastError());
+  }
+  std::vector<double> lh;
+  Tens Z;
+  int64_t N = 0;
+  eigh_dc(c, H, nh, lh, Z, N);
+  // real eigenvalues = the nh smallest (pads are above the spectrum); positive ones, descending
+  std::vector<int> idx((size_t)N);
+  for (int64_t i = 0; i < N; ++i) idx[(size_t)i] = (int)i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lh[x] < lh[y]; });
+  idx.resize((size_t)nh);
+  double fro2 = 0.0;
+  for (int i : idx) fro2 += 0.5 * lh[i] * lh[i];
+  const double thr = 16.0 * 2.220446049250313e-16 * std::sqrt(fro2);
+  std::vector<int> pos;
+  for (auto it = idx.rbegin(); it != idx.rend() && (int64_t)pos.size() < kk; ++it)
+    if (lh[*it] > thr) pos.push_back(*it);
+  const int64_t r = (int64_t)pos.size();
+  std::vector<double> sval((size_t)kk, 0.0);
+  for (int64_t i = 0; i < r; ++i) sval[(size_t)i] = lh[pos[(size_t)i]];
+  SvdResult res;
+  res.U = t_alloc(c, {m, kk}, true);
+  res.V = t_alloc(c, {n, kk}, true);
+  res.S = t_alloc(c, {kk});
+  h2d(c, res.S.p, sval.data(), (size_t)kk);
+  if (r > 0) {
+    Tens meta = t_alloc(c, {r / 2 + 2});
+    int* dpos = reinterpret_cast<int*>(meta.p);
+    TNAD_CUDA(cudaMemcpyAsync(dpos, pos.data(), (size_t)r * sizeof(int), cudaMemcpyHostToDevice, st));
+    k_gather_jw<<<(int)r, 128, 0, st>>>(Z.p, N, dpos, m, n, res.U.p, res.V.p);
+    c->launches++;
+    TNAD_CUDA(cudaGetLastError());
+  }
+  sync(c);
+  res.s_host = sval;
+  res.null_thr = thr;
+  res.rank_left = r;
+  res.rank_right = r;
   res.sweeps = 0;
   return res;
 }
