@@ -611,3 +611,20 @@ def test_svd_sym_direct_solver_degenerate_inputs(ctx, kind, monkeypatch):
     assert np.abs(s - ref).max() <= 1e-12 * scale
     assert np.abs((u * s) @ v.T - a).max() <= 1e-12 * scale
     assert np.abs(u.T @ u - np.eye(n)).max() <= 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("beta", [0.3, 0.44, 0.6])
+def test_trg_same_with_both_svd_routes(ctx, beta, monkeypatch):
+    """TRG value + gradient through the one-sided Jacobi SVD and through the Jordan-Wielandt / direct-eigensolver route
+    (rank-deficient splits: the null triplets enter svd_back only through the projectors)."""
+    a = T.model_tensor(T.Ising(), beta)
+    out = {}
+    for mode in ("jacobi", "dc"):
+        monkeypatch.setenv("TNAD_TRG_SVD", mode)
+        out[mode] = T.trg_value_and_grad(a, 12, 9, ctx=ctx)
+    (l1, g1), (l2, g2) = out["jacobi"], out["dc"]
+    assert abs(l1 - l2) <= 1e-12 * abs(l1)
+    assert np.abs(g1 - g2).max() <= 1e-9 * np.abs(g1).max()
+    lo, go = O.trg_value_and_grad(a, 12, 9)
+    assert abs(l2 - lo) <= 1e-10 * abs(lo) and np.abs(g2 - go).max() <= 1e-8 * np.abs(go).max()
