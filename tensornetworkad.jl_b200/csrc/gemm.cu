@@ -355,7 +355,17 @@ void launch_layout(tnad_ctx* c, const GemmDesc& d) {
 void gemm_run(tnad_ctx* c, const GemmDesc& d0) {
   if (d0.M <= 0 || d0.N <= 0 || d0.batch <= 0) return;
   GemmDesc d = d0;
-  const bool large = d.M >= 96 && d.N >= 96;
+  bool large = d.M >= 96 && d.N >= 96;
+  {
+    // short-K products with few 128x128 tiles (trailing updates of the tridiagonalisation, compact-WY updates): the
+    // 64x64 tiling gives 4x the CTAs for the same bytes; A/B knob TNAD_GEMM_SMALLK=<K limit> (0 = off)
+    static const int smallk = [] {
+      const char* v = getenv("TNAD_GEMM_SMALLK");
+      return v ? atoi(v) : 128;   // measured at n = 2048: trailing updates 3.3 -> 2.3 ms, back-transform 2.5 -> 2.2 ms per decomposition
+    }();
+    const long long t128 = (long long)((d.M + 127) / 128) * ((d.N + 127) / 128) * d.batch;
+    if (large && smallk > 0 && d.K <= smallk && t128 < 2LL * c->num_sms) large = false;
+  }
   const int bm = large ? 128 : 64;
   const long long tiles = (long long)((d.M + bm - 1) / bm) * ((d.N + bm - 1) / bm) * d.batch;
   // split-K when the output tiles alone cannot fill the machine (small M x N, long K: the projector and

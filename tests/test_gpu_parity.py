@@ -625,7 +625,12 @@ def test_trg_same_with_both_svd_routes(ctx, beta, monkeypatch):
         out[mode] = T.trg_value_and_grad(a, 12, 9, ctx=ctx)
     (l1, g1), (l2, g2) = out["jacobi"], out["dc"]
     assert abs(l1 - l2) <= 1e-12 * abs(l1)
-    assert np.abs(g1 - g2).max() <= 1e-9 * np.abs(g1).max()
+    # full gradient tensor: components along rank-lifting / degenerate-pair directions amplify 1e-15 differences of the
+    # singular vectors by 1/(s_i^2 - s_j^2) (the same directions in which oracle and Zygote golden differ by percents);
+    # the physical derivative must agree tightly
+    assert np.abs(g1 - g2).max() <= 1e-6 * np.abs(g1).max()
+    da_ = O.dmodel_tensor_ising(beta)
+    assert abs(np.sum(g1 * da_) - np.sum(g2 * da_)) <= 1e-10 * abs(np.sum(g1 * da_))
     # against the oracle: the value and the physical derivative d lnZ / d beta (directions that lift the rank of a split
     # are ill-defined in the reference itself, see test_trg_gradient_published)
     lo, go = O.trg_value_and_grad(a, 12, 9)
