@@ -283,9 +283,12 @@ def run_ours(args):
             # kernel k_sytrd_panel (timed in the `pivot_eig` slot).  Its algorithmic traffic is the trailing matrix read
             # once per reflector: 8 * sum_j (n-j-1)^2 bytes per decomposition (~ 8 n^3 / 3), DESIGN.md section 4.2.
             n_mat = CHI * D_IPEPS ** 2
-            panels = -(-(n_mat - 2) // 32)
+            # columns [0, j_tail) run in the grid-wide panel kernel (32 per launch), the last t = n - j_tail <= 416 columns
+            # in ONE launch of the cluster kernel, which loads the trailing matrix once into distributed shared memory
+            j_tail = ((n_mat - 416 + 31) // 32) * 32 if n_mat > 416 else 0
+            panels = j_tail // 32 + 1
             n_svd = pe["launches"] / panels if panels else 0
-            bytes_svd = 8.0 * sum((n_mat - j - 1) ** 2 for j in range(n_mat - 2))
+            bytes_svd = 8.0 * sum((n_mat - j - 1) ** 2 for j in range(j_tail)) + 8.0 * (n_mat - j_tail) ** 2
             gbs = bytes_svd * n_svd / (pe["ms"] * 1e-3) / 1e9 if pe["ms"] > 0 else 0.0
             hbm = float(pk.get("hbm_gbs", 0.0)) or None
             tr = None
@@ -293,14 +296,14 @@ def run_ours(args):
                 with open(tpath) as f:
                     tr = json.load(f).get("k_sytrd_panel_dram_bytes_per_launch")
             roof = {"bound": "hbm",
-                    "kernel": "k_sytrd_panel (persistent cooperative Householder tridiagonalisation panel: per column one "
-                              "symmetric matrix-vector product over the trailing matrix, two grid barriers; FP64 vector)",
+                    "kernel": "k_sytrd_panel1 (+ k_sytrd_tail_cluster for the last 416 columns): persistent cooperative Householder "
+                              "tridiagonalisation, per column one matrix-vector product over the trailing matrix and one grid-wide exchange; FP64 vector",
                     "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm if hbm else None, "traffic": tr,
                     "bytes_per_launch": bytes_svd / panels if panels else None,
                     "avg_launch_us": 1e3 * pe["ms"] / pe["launches"] if pe["launches"] else None,
                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs [{pk_kind}]",
-                    "note": "latency bound at n=2048: the 33.5 MB trailing matrix is L2 resident, each of the 2046 columns costs two grid-wide "
-                            "barriers and ~4 dependent L2 round trips; the fraction says how far the column loop is from streaming the matrix at HBM speed",
+                    "note": "synchronisation bound at n=2048: the 33.5 MB trailing matrix is L2 resident, every column costs one grid-wide exchange "
+                            "(~3 L2 round trips) plus gather and matvec; the fraction says how far the column loop is from streaming the matrix at HBM speed",
                     "kernel_ms_instrumented_pass": {("sytrd_panel" if k == "pivot_eig" else k): round(v["ms"], 3) for k, v in kt.items()},
                     "kernel_launches": {("sytrd_panel" if k == "pivot_eig" else k): v["launches"] for k, v in kt.items()},
                     "largest_family_by_device_time": "sytrd_panel" if dom == "pivot_eig" else dom,

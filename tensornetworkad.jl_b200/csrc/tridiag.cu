@@ -17,6 +17,7 @@
 #include "eigdc.h"
 #include <algorithm>
 #include <numeric>
+#include <cooperative_groups.h>
 
 namespace tnad {
 
@@ -312,10 +313,8 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
   double* Vs = ajns + NL;        // NL x 32
   double* Ws = Vs + NL * S1_NB;  // NL x 32
   double* sums = Ws + NL * S1_NB;   // 80
-  double* sv = sums + 80;
-  double* sw = sv + S1_NB;
-  double* svp = sw + S1_NB;      // [2][32] (column parity)
-  double* swp = svp + 2 * S1_NB; // [2][32]
+  double* svp = sums + 80;       // V_k'v_p of the previous column, [2][32] (column parity)
+  double* swp = svp + 2 * S1_NB; // W_k'v_p, [2][32]
   double* vjn = swp + 2 * S1_NB; // V[jn, :]
   double* wjn = vjn + S1_NB;     // W[jn, :] (final values)
   double* vjr = wjn + S1_NB;     // V[j, :]
@@ -819,6 +818,141 @@ __global__ void __launch_bounds__(ST_NT, 1) k_sytrd_panel1(const double* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tail of the tridiagonalisation on ONE thread-block cluster.  Once the trailing matrix fits into the shared memory of
+// a cluster (t = n - j_start <= 416 with 8 CTAs), a grid-wide exchange per column (~3 L2 round trips, 9 us) is the wrong
+// tool: the cluster keeps the whole trailing matrix in distributed shared memory (CTA k owns the columns c = k mod 8),
+// exchanges v and the matvec partials through DSMEM and synchronises with two hardware cluster barriers per column.  Unblocked
+// dsytd2-style update A -= v w' + w v' directly on the resident matrix (no panels, no trailing GEMM).
+constexpr int TC_CS = 8;       // portable cluster size
+constexpr int TC_NT = 512;
+constexpr int TC_TMAX = 416;   // ceil(t/8) * t doubles of columns + work vectors must fit into 227 KB
+__global__ void __launch_bounds__(TC_NT, 1) k_sytrd_tail_cluster(const double* __restrict__ A, long long lda, int n, int j_start,
+                                                                 double* Vh, long long ldv, double* tau, double* dd,
+                                                                 double* ee) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) double sm[];
+  const int t = n - j_start;                 // order of the resident trailing matrix
+  const int rank = (int)cluster.block_rank(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nslot = (t + TC_CS - 1) / TC_CS;
+  double* cols = sm;                          // [nslot][t]: column c = rank + slot * 8 (tail coordinates)
+  double* vbuf = cols + (size_t)nslot * t;    // [2][t]  reflector (parity)
+  double* ybuf = vbuf + 2 * t;                // [t]     A v, assembled by the slice owners of all CTAs
+  double* ubuf = ybuf + t;                    // [t]     this CTA's matvec partial
+  double* wbuf = ubuf + t;                    // [t]
+  double* scal = wbuf + t;                    // [2][4] tau, beta (parity); [8..16) gamma partials; [16..) reduction scratch
+  for (int idx = tid; idx < nslot * t; idx += TC_NT) {
+    const int slot = idx / t, r = idx - slot * t, cl = rank + slot * TC_CS;
+    cols[idx] = (cl < t) ? A[(long long)(j_start + r) + (long long)(j_start + cl) * lda] : 0.0;
+  }
+  __syncthreads();
+  cluster.sync();
+  for (int jj = 0; jj + 2 < t; ++jj) {
+    const int par = jj & 1, owner = jj % TC_CS, j1 = jj + 1;
+    double* v = vbuf + par * t;
+    // ---- 1. owner: reflector from its resident column jj, broadcast v and (tau, beta) to every CTA ----
+    if (rank == owner) {
+      const double* x = cols + (size_t)(jj / TC_CS) * t;
+      double ss = 0.0;
+      for (int r = j1 + 1 + tid; r < t; r += TC_NT) ss += x[r] * x[r];
+      ss = warp_sum(ss);
+      if (lane == 0) scal[16 + warp] = ss;
+      __syncthreads();
+      double xn2 = 0.0;
+      for (int w = 0; w < TC_NT / 32; ++w) xn2 += scal[16 + w];
+      const double alpha = x[j1];
+      double beta, tj, sc;
+      if (!(xn2 > 0.0)) {
+        beta = alpha;
+        tj = 0.0;
+        sc = 0.0;
+      } else {
+        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        const double amb = alpha - beta, rr = 1.0 / (beta * amb);
+        sc = rr * beta;
+        tj = -amb * (rr * amb);
+      }
+      for (int idx = tid; idx < t * TC_CS; idx += TC_NT) {
+        const int dst = idx / t, r = idx - dst * t;
+        const double val = (r < j1) ? 0.0 : (r == j1 ? 1.0 : x[r] * sc);
+        cluster.map_shared_rank(v, dst)[r] = val;
+      }
+      if (tid < TC_CS) {
+        double* rs = cluster.map_shared_rank(scal, tid);
+        rs[par * 4 + 0] = tj;
+        rs[par * 4 + 1] = beta;
+      }
+      for (int r = j1 + tid; r < t; r += TC_NT) Vh[(long long)(j_start + r) + (long long)(j_start + jj) * ldv] = (r == j1) ? 1.0 : x[r] * sc;
+      if (tid == 0) {
+        dd[j_start + jj] = x[jj];
+        ee[j_start + jj] = beta;
+        tau[j_start + jj] = tj;
+      }
+    }
+    cluster.sync();   // #1: v, tau in every CTA
+    const double tj = scal[par * 4 + 0];
+    // ---- 2. matvec partial over the owned columns, then every CTA reduces its row slice through DSMEM ----
+    {
+      const int s0 = (j1 > rank) ? (j1 - rank + TC_CS - 1) / TC_CS : 0;     // first owned slot with column >= j1
+      for (int r = j1 + tid; r < t; r += TC_NT) {
+        double acc = 0.0;
+        for (int slot = s0; slot < nslot; ++slot) {
+          const int cl = rank + slot * TC_CS;
+          if (cl < t) acc += cols[(size_t)slot * t + r] * v[cl];
+        }
+        ubuf[r] = acc;
+      }
+    }
+    cluster.sync();   // #2: all partials written
+    {
+      // every CTA assembles the full y = A v itself: 8 DSMEM loads per row, all in flight (one row per thread), which
+      // saves the third cluster barrier a slice-wise reduction + broadcast would need
+      double gpart = 0.0;
+      for (int r = j1 + tid; r < t; r += TC_NT) {
+        double x0[TC_CS];
+#pragma unroll
+        for (int src = 0; src < TC_CS; ++src) x0[src] = cluster.map_shared_rank(ubuf, src)[r];
+        double y = 0.0;
+#pragma unroll
+        for (int src = 0; src < TC_CS; ++src) y += x0[src];
+        ybuf[r] = y;
+        gpart += y * v[r];
+      }
+      gpart = warp_sum(gpart);
+      if (lane == 0) scal[16 + warp] = gpart;
+      __syncthreads();
+      double gamma = 0.0;
+      for (int w = 0; w < TC_NT / 32; ++w) gamma += scal[16 + w];
+      const double c2 = 0.5 * tj * tj * gamma;
+      for (int r = j1 + tid; r < t; r += TC_NT) wbuf[r] = tj * ybuf[r] - c2 * v[r];
+      __syncthreads();
+      // ---- 3. rank-2 update of the owned columns c >= j1, rows >= j1 ----
+      const int s0 = (j1 > rank) ? (j1 - rank + TC_CS - 1) / TC_CS : 0;
+      const int nr = t - j1;
+      for (int idx = tid; idx < (nslot - s0) * nr; idx += TC_NT) {
+        const int slot = s0 + idx / nr, r = j1 + (idx - (idx / nr) * nr), cl = rank + slot * TC_CS;
+        if (cl < t) cols[(size_t)slot * t + r] -= v[r] * wbuf[cl] + wbuf[r] * v[cl];
+      }
+      __syncthreads();
+    }
+  }
+  // the last 2 x 2 block
+  {
+    const int c2i = t - 2, c1i = t - 1;
+    if (t >= 2 && rank == c2i % TC_CS && tid == 0) {
+      const double* x = cols + (size_t)(c2i / TC_CS) * t;
+      dd[j_start + c2i] = x[c2i];
+      ee[j_start + c2i] = x[c1i];
+    }
+    if (rank == c1i % TC_CS && tid == 0) {
+      const double* x = cols + (size_t)(c1i / TC_CS) * t;
+      dd[j_start + c1i] = x[c1i];
+    }
+  }
+  cluster.sync();   // nobody may exit while its shared memory can still be addressed remotely
+}
+
 __global__ void k_sytrd_tail(const double* A, long long lda, int n, double* dd, double* ee) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (n >= 2) {
@@ -925,8 +1059,14 @@ Tens view2(double* p, int64_t rows, int64_t cols, int64_t ld) {
 void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t ldv, double* tau, double* dd, double* ee) {
   TNAD_REQUIRE(n >= 1, "sytrd: empty matrix");
   const int nb = 32;
-  const int64_t nref = n >= 3 ? n - 2 : 0;
   cudaStream_t st = c->stream;
+  // columns [0, j_tail) go through the grid-wide panel kernel, the rest (trailing order t <= 416) through the cluster kernel
+  int64_t j_tail = n;
+  if (env_i("TNAD_SYTRD_TAIL", 1) && n >= 3) {
+    j_tail = n > TC_TMAX ? ((n - TC_TMAX + nb - 1) / nb) * nb : 0;
+    if (n - j_tail < 3) j_tail = n;
+  }
+  const int64_t nref = j_tail < n ? j_tail : (n >= 3 ? n - 2 : 0);    // reflector columns done by the panel kernel
   if (nref > 0) {
     const size_t smem = (size_t)(n + 4 * nb + ST_PJ + ST_NW + 16) * sizeof(double);
     TNAD_REQUIRE(n <= (int64_t)ST_CH * ST_PJ, "sytrd: n too large");
@@ -939,7 +1079,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     const int64_t ldp = n;
     const bool one_barrier = env_i("TNAD_SYTRD_1B", 1) != 0;
     const int64_t NQ = (n + 3) / 4, NL = 4 * ((NQ + G - 1) / G);
-    const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 10 * S1_NB + 24) * sizeof(double);
+    const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 8 * S1_NB + 24) * sizeof(double);
     Tens upart, spart1, pub, redo, prof;
     size_t smem_total = 0;
     int cache_cap_max = 0;
@@ -1030,9 +1170,36 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
               (double)ph[5] / nref, (double)ph[6] / nref);
     }
   }
-  k_sytrd_tail<<<1, 32, 0, st>>>(A, lda, (int)n, dd, ee);
-  c->launches++;
-  TNAD_CUDA(cudaGetLastError());
+  if (j_tail < n) {
+    const int64_t t = n - j_tail, nslot = (t + TC_CS - 1) / TC_CS;
+    const size_t smem = (size_t)(nslot * t + 5 * t + 64) * sizeof(double);
+    TNAD_REQUIRE(smem <= 232448 - 256, "sytrd: tail does not fit into the cluster");
+    TNAD_CUDA(cudaFuncSetAttribute(k_sytrd_tail_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(TC_CS);
+    cfg.blockDim = dim3(TC_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TC_CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const double* Ac = A;
+    long long lda_ = lda, ldv_ = ldv;
+    int ni = (int)n, jt = (int)j_tail;
+    {
+      KTimer kt(c, KF_EIG);
+      TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_sytrd_tail_cluster, Ac, lda_, ni, jt, Vh, ldv_, tau, dd, ee));
+    }
+    c->launches++;
+  } else {
+    k_sytrd_tail<<<1, 32, 0, st>>>(A, lda, (int)n, dd, ee);
+    c->launches++;
+    TNAD_CUDA(cudaGetLastError());
+  }
 }
 
 // Number of columns the reflector store Vh (and tau) must have: panels of the back-transformation are read as a
