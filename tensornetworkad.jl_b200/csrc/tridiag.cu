@@ -829,8 +829,16 @@ constexpr int TC_NT = 512;
 constexpr int TC_TMAX = 416;   // ceil(t/8) * t doubles of columns + work vectors must fit into 227 KB
 __global__ void __launch_bounds__(TC_NT, 1) k_sytrd_tail_cluster(const double* __restrict__ A, long long lda, int n, int j_start,
                                                                  double* Vh, long long ldv, double* tau, double* dd,
-                                                                 double* ee) {
+                                                                 double* ee, long long* prof) {
   namespace cg = cooperative_groups;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#define TC_PROF(slot)                          \
+  if (prof) {                                  \
+    const long long tn = clock64();            \
+    pacc[slot] += tn - tprev;                  \
+    tprev = tn;                                \
+  }
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double sm[];
   const int t = n - j_start;                 // order of the resident trailing matrix
@@ -846,6 +854,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_sytrd_tail_cluster(const double* _
     const int slot = idx / t, r = idx - slot * t, cl = rank + slot * TC_CS;
     cols[idx] = (cl < t) ? A[(long long)(j_start + r) + (long long)(j_start + cl) * lda] : 0.0;
   }
+  for (int idx = tid; idx < 2 * t; idx += TC_NT) vbuf[idx] = 0.0;
   __syncthreads();
   cluster.sync();
   for (int jj = 0; jj + 2 < t; ++jj) {
@@ -873,38 +882,47 @@ __global__ void __launch_bounds__(TC_NT, 1) k_sytrd_tail_cluster(const double* _
         sc = rr * beta;
         tj = -amb * (rr * amb);
       }
-      for (int idx = tid; idx < t * TC_CS; idx += TC_NT) {
-        const int dst = idx / t, r = idx - dst * t;
-        const double val = (r < j1) ? 0.0 : (r == j1 ? 1.0 : x[r] * sc);
-        cluster.map_shared_rank(v, dst)[r] = val;
-      }
       if (tid < TC_CS) {
         double* rs = cluster.map_shared_rank(scal, tid);
         rs[par * 4 + 0] = tj;
         rs[par * 4 + 1] = beta;
       }
-      for (int r = j1 + tid; r < t; r += TC_NT) Vh[(long long)(j_start + r) + (long long)(j_start + jj) * ldv] = (r == j1) ? 1.0 : x[r] * sc;
+      // rows >= jj only: the entries below were zeroed when their column was processed (v buffers start zeroed)
+      for (int r = jj + tid; r < t; r += TC_NT) {
+        const double val = (r < j1) ? 0.0 : (r == j1 ? 1.0 : x[r] * sc);
+#pragma unroll
+        for (int dst = 0; dst < TC_CS; ++dst) cluster.map_shared_rank(v, dst)[r] = val;
+        if (r >= j1) Vh[(long long)(j_start + r) + (long long)(j_start + jj) * ldv] = val;
+      }
       if (tid == 0) {
         dd[j_start + jj] = x[jj];
         ee[j_start + jj] = beta;
         tau[j_start + jj] = tj;
       }
     }
+    TC_PROF(0)
     cluster.sync();   // #1: v, tau in every CTA
+    TC_PROF(1)
     const double tj = scal[par * 4 + 0];
     // ---- 2. matvec partial over the owned columns, then every CTA reduces its row slice through DSMEM ----
     {
       const int s0 = (j1 > rank) ? (j1 - rank + TC_CS - 1) / TC_CS : 0;     // first owned slot with column >= j1
+      const int s1 = (t - rank + TC_CS - 1) / TC_CS;
       for (int r = j1 + tid; r < t; r += TC_NT) {
-        double acc = 0.0;
-        for (int slot = s0; slot < nslot; ++slot) {
-          const int cl = rank + slot * TC_CS;
-          if (cl < t) acc += cols[(size_t)slot * t + r] * v[cl];
+        double a0 = 0.0, a1 = 0.0;
+        const double* cp = cols + (size_t)s0 * t + r;
+        int cl = rank + s0 * TC_CS, slot = s0;
+        for (; slot + 1 < s1; slot += 2, cp += 2 * t, cl += 2 * TC_CS) {
+          a0 += cp[0] * v[cl];
+          a1 += cp[t] * v[cl + TC_CS];
         }
-        ubuf[r] = acc;
+        if (slot < s1) a0 += cp[0] * v[cl];
+        ubuf[r] = a0 + a1;
       }
     }
+    TC_PROF(2)
     cluster.sync();   // #2: all partials written
+    TC_PROF(3)
     {
       // every CTA assembles the full y = A v itself: 8 DSMEM loads per row, all in flight (one row per thread), which
       // saves the third cluster barrier a slice-wise reduction + broadcast would need
@@ -927,16 +945,23 @@ __global__ void __launch_bounds__(TC_NT, 1) k_sytrd_tail_cluster(const double* _
       const double c2 = 0.5 * tj * tj * gamma;
       for (int r = j1 + tid; r < t; r += TC_NT) wbuf[r] = tj * ybuf[r] - c2 * v[r];
       __syncthreads();
+      TC_PROF(4)
       // ---- 3. rank-2 update of the owned columns c >= j1, rows >= j1 ----
       const int s0 = (j1 > rank) ? (j1 - rank + TC_CS - 1) / TC_CS : 0;
-      const int nr = t - j1;
-      for (int idx = tid; idx < (nslot - s0) * nr; idx += TC_NT) {
-        const int slot = s0 + idx / nr, r = j1 + (idx - (idx / nr) * nr), cl = rank + slot * TC_CS;
-        if (cl < t) cols[(size_t)slot * t + r] -= v[r] * wbuf[cl] + wbuf[r] * v[cl];
+      const int s1 = (t - rank + TC_CS - 1) / TC_CS;        // owned slots with a column < t
+      for (int r = j1 + tid; r < t; r += TC_NT) {            // one row per thread, v[r], w[r] in registers
+        const double vr = v[r], wr = wbuf[r];
+        double* cp = cols + (size_t)s0 * t + r;
+        int cl = rank + s0 * TC_CS;
+#pragma unroll 4
+        for (int slot = s0; slot < s1; ++slot, cp += t, cl += TC_CS) *cp -= vr * wbuf[cl] + wr * v[cl];
       }
       __syncthreads();
+      TC_PROF(5)
     }
   }
+  if (prof && rank == 0 && tid == 0)
+    for (int q = 0; q < 6; ++q) prof[q] = pacc[q];
   // the last 2 x 2 block
   {
     const int c2i = t - 2, c1i = t - 1;
@@ -1190,11 +1215,21 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     const double* Ac = A;
     long long lda_ = lda, ldv_ = ldv;
     int ni = (int)n, jt = (int)j_tail;
+    Tens tp = t_alloc(c, {8}, true);
+    long long* tprof = env_i("TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(tp.p) : nullptr;
     {
       KTimer kt(c, KF_EIG);
-      TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_sytrd_tail_cluster, Ac, lda_, ni, jt, Vh, ldv_, tau, dd, ee));
+      TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_sytrd_tail_cluster, Ac, lda_, ni, jt, Vh, ldv_, tau, dd, ee, tprof));
     }
     c->launches++;
+    if (tprof) {
+      long long ph[8];
+      sync(c);
+      TNAD_CUDA(cudaMemcpy(ph, tp.p, sizeof(ph), cudaMemcpyDeviceToHost));
+      const double nc = (double)std::max<int64_t>(1, t - 2);
+      fprintf(stderr, "[tnad dc] cluster tail t=%lld cycles/column (rank 0): reflector %.0f  sync1 %.0f  matvec %.0f  sync2 %.0f  assemble+w %.0f  update %.0f\n",
+              (long long)t, ph[0] / nc, ph[1] / nc, ph[2] / nc, ph[3] / nc, ph[4] / nc, ph[5] / nc);
+    }
   } else {
     k_sytrd_tail<<<1, 32, 0, st>>>(A, lda, (int)n, dd, ee);
     c->launches++;
