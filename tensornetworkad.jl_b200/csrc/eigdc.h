@@ -18,7 +18,7 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose);
 // triplets are formed (rank_left = rank_right = r)
 SvdResult svd_general_dc(tnad_ctx* c, const Tens& A);
 // Solver selection for symmetric inputs: TNAD_SYMEIG = 1 block Jacobi (symeig.cu), 2 tridiagonal divide and conquer;
-// default: divide and conquer from n >= TNAD_DC_MIN (96) on (measured crossover: equal at n = 64, 1.5x faster at 96).
+// default: divide and conquer from n >= TNAD_DC_MIN (48) on (measured with the cluster kernel: 0.88 vs 1.34 ms at n = 64).
 SvdResult svd_symmetric_auto(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* Q0 = nullptr);
 
 }  // namespace tnad
