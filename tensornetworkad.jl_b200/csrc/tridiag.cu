@@ -860,50 +860,59 @@ __global__ void __launch_bounds__(TC_NT, 1) k_sytrd_tail_cluster(const double* _
   for (int jj = 0; jj + 2 < t; ++jj) {
     const int par = jj & 1, owner = jj % TC_CS, j1 = jj + 1;
     double* v = vbuf + par * t;
-    // ---- 1. owner: reflector from its resident column jj, broadcast v and (tau, beta) to every CTA ----
+    // ---- 1. owner: broadcast the RAW column first (the DSMEM stores drain while the norm, the square root and the
+    // division are computed), then the three scalars; every CTA scales its own copy after the barrier ----
     if (rank == owner) {
       const double* x = cols + (size_t)(jj / TC_CS) * t;
       double ss = 0.0;
-      for (int r = j1 + 1 + tid; r < t; r += TC_NT) ss += x[r] * x[r];
+      for (int r = jj + tid; r < t; r += TC_NT) {
+        const double xr = (r < j1) ? 0.0 : x[r];
+#pragma unroll
+        for (int dst = 0; dst < TC_CS; ++dst) cluster.map_shared_rank(v, dst)[r] = xr;
+        if (r > j1) ss += xr * xr;
+      }
       ss = warp_sum(ss);
       if (lane == 0) scal[16 + warp] = ss;
       __syncthreads();
-      double xn2 = 0.0;
-      for (int w = 0; w < TC_NT / 32; ++w) xn2 += scal[16 + w];
-      const double alpha = x[j1];
-      double beta, tj, sc;
-      if (!(xn2 > 0.0)) {
-        beta = alpha;
-        tj = 0.0;
-        sc = 0.0;
-      } else {
-        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-        const double amb = alpha - beta, rr = 1.0 / (beta * amb);
-        sc = rr * beta;
-        tj = -amb * (rr * amb);
-      }
       if (tid < TC_CS) {
-        double* rs = cluster.map_shared_rank(scal, tid);
+        double xn2 = 0.0;
+        for (int w = 0; w < TC_NT / 32; ++w) xn2 += scal[16 + w];
+        const double alpha = x[j1];
+        double beta, tj, sc;
+        if (!(xn2 > 0.0)) {
+          beta = alpha;
+          tj = 0.0;
+          sc = 0.0;
+        } else {
+          beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+          const double amb = alpha - beta, rr = 1.0 / (beta * amb);
+          sc = rr * beta;
+          tj = -amb * (rr * amb);
+        }
+        double* rs = cluster.map_shared_rank(scal, tid);   // thread k serves CTA k (8 threads repeat the scalar math)
         rs[par * 4 + 0] = tj;
         rs[par * 4 + 1] = beta;
-      }
-      // rows >= jj only: the entries below were zeroed when their column was processed (v buffers start zeroed)
-      for (int r = jj + tid; r < t; r += TC_NT) {
-        const double val = (r < j1) ? 0.0 : (r == j1 ? 1.0 : x[r] * sc);
-#pragma unroll
-        for (int dst = 0; dst < TC_CS; ++dst) cluster.map_shared_rank(v, dst)[r] = val;
-        if (r >= j1) Vh[(long long)(j_start + r) + (long long)(j_start + jj) * ldv] = val;
-      }
-      if (tid == 0) {
-        dd[j_start + jj] = x[jj];
-        ee[j_start + jj] = beta;
-        tau[j_start + jj] = tj;
+        rs[par * 4 + 2] = sc;
+        if (tid == 0) {
+          dd[j_start + jj] = x[jj];
+          ee[j_start + jj] = beta;
+          tau[j_start + jj] = tj;
+        }
       }
     }
     TC_PROF(0)
     cluster.sync();   // #1: v, tau in every CTA
     TC_PROF(1)
     const double tj = scal[par * 4 + 0];
+    {
+      const double sc = scal[par * 4 + 2];
+      for (int r = j1 + tid; r < t; r += TC_NT) {
+        const double val = (r == j1) ? 1.0 : v[r] * sc;
+        v[r] = val;
+        if (rank == owner) Vh[(long long)(j_start + r) + (long long)(j_start + jj) * ldv] = val;
+      }
+      __syncthreads();
+    }
     // ---- 2. matvec partial over the owned columns, then every CTA reduces its row slice through DSMEM ----
     {
       const int s0 = (j1 > rank) ? (j1 - rank + TC_CS - 1) / TC_CS : 0;     // first owned slot with column >= j1
