@@ -102,7 +102,9 @@ TrgSplit trg_split(tnad_ctx* c, const Tens& t4, int64_t dmax, double tol) {
     // forces the one-sided block Jacobi path)
     const int64_t mm = t4.dim[0] * t4.dim[1], nn = t4.dim[2] * t4.dim[3];
     const char* ev = getenv("TNAD_TRG_SVD");
-    const bool jac = (ev && ev[0] == 'j') || mm + nn < 96;
+    int coop = 0;
+    TNAD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    const bool jac = (ev && ev[0] == 'j') || mm + nn < 96 || !coop;
     sp.svd = jac ? svd_jacobi(c, t4, false, nullptr, /*complete_null=*/false) : svd_general_dc(c, t4);
   }
   const int64_t m = t4.dim[0] * t4.dim[1], n = t4.dim[2] * t4.dim[3];

@@ -1440,7 +1440,11 @@ SvdResult svd_general_dc(tnad_ctx* c, const Tens& A4) {
 SvdResult svd_symmetric_auto(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* Q0) {
   const int mode = env_i("TNAD_SYMEIG", -1);
   const int64_t n = A.dim[0];
-  const bool dc = mode == 2 || (mode < 0 && n >= env_i("TNAD_DC_MIN", 48));
+  // the direct solver needs cooperative (co-resident) launches; a device / partition without them keeps the Jacobi path
+  int coop = 0;
+  TNAD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+  TNAD_REQUIRE(coop || mode != 2, "TNAD_SYMEIG=2 needs cooperative kernel launches, which this device does not support");
+  const bool dc = coop && (mode == 2 || (mode < 0 && n >= env_i("TNAD_DC_MIN", 48)));
   return dc ? svd_symmetric_dc(c, A, sym_add_transpose) : svd_symmetric(c, A, sym_add_transpose, Q0);
 }
 
