@@ -4,15 +4,21 @@
 //
 //   A = Q T Q',  Q = H_0 H_1 ... H_{n-3},  H_j = I - tau_j v_j v_j'
 //
-// k_sytrd_panel is ONE persistent cooperative kernel per panel of nb columns (dlatrd-style blocking, published
-// LAPACK algorithm): all CTAs stay resident and meet at a global barrier twice per column.
-//   phase B  every warp takes trailing columns c and forms p_c = A22[:, c] . v   (A22 is symmetric and stored in
-//            full, so the matrix-vector product is a set of independent, coalesced column dots - no atomics, no
-//            cross-CTA partial sums, bit-reproducible); the 2i panel columns V, W are dotted with v in the same pass.
-//   phase C  (rows cyclic over warps) w = tau (p - V W'v - W V'v) - 1/2 tau^2 (p'v) v, then the NEXT column of A
-//            is brought up to date with the pending rank-2i update and its norm is reduced for the next reflector.
-// The rank-2nb trailing update A22 -= V W' + W V' between panels is one DMMA GEMM (contract) with K = 2 nb.
-// The dominant cost is phase B: 8 n^3 / 3 bytes of matrix reads (HBM/L2 bound), see DESIGN.md.
+// Three kernels share the work (sytrd() below picks per column range):
+//   k_sytrd_panel1        default for the columns whose trailing matrix does not fit a cluster: ONE persistent cooperative
+//                         kernel per panel of 32 columns, ONE grid-wide exchange per column (index ownership, matvec by
+//                         column ownership on a vector that does not need the previous column's pending scalar, cancellation
+//                         guard, sector-packed exchange buffers, TMA-staged shared-memory cache of the CTA's columns).
+//   k_sytrd_tail_cluster  the last <= 416 columns (and whole problems up to that order) on one thread-block cluster with the
+//                         trailing matrix resident in distributed shared memory (unblocked dsytd2 update, DSMEM exchange,
+//                         two hardware cluster barriers per column).
+//   k_sytrd_panel         the first version (A/B switch TNAD_SYTRD_1B=0): dlatrd-style, two grid barriers per column;
+//                         phase B forms p_c = A22[:, c] . v as independent coalesced column dots (A22 is stored in full),
+//                         phase C forms w and brings the next column of A up to date.
+// The rank-64 trailing update A22 -= V W' + W V' between panels is one DMMA GEMM (contract) with K = 64.
+// Algorithmic traffic: the trailing matrix once per column, 8 n^3 / 3 bytes per decomposition.
+// Also here: the compact-WY back-transformation (apply_q), the symmetric driver (svd_symmetric_dc) and the general
+// driver through the Jordan-Wielandt embedding (svd_general_dc).
 #include "drivers.h"
 #include "eigdc.h"
 #include <algorithm>
