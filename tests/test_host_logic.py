@@ -357,3 +357,23 @@ def test_one_barrier_tridiagonalisation_prototype(kind):
     assert np.abs(Q @ Tm @ Q.T - a).max() < 1e-13 * nrm
     if kind == "low_rank":
         assert P.REDO[0] >= 1          # the cancellation guard must fire at the rank boundary
+
+
+# ---- bench.py contract: the committed result line carries every key the driver reads -------------------------------
+def test_recorded_bench_line_has_contract_keys():
+    import json
+    path = os.path.join(ROOT, "profiles", "r1_bench_n1.json")
+    line = json.loads(open(path).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["dtype"] == "f64" and line["higher_is_better"] is False and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    r = line["roofline"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r)
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = line["cpu_baseline"]
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("port", "reference")
+    assert line["gpu_launches"] > 0 and line["clocks"]["reasons"] == []
