@@ -377,3 +377,16 @@ def test_recorded_bench_line_has_contract_keys():
     c = line["cpu_baseline"]
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("port", "reference")
     assert line["gpu_launches"] > 0 and line["clocks"]["reasons"] == []
+
+
+def test_golub_kahan_prototype():
+    P = _load_tool("gebrd_proto")
+    rng = np.random.default_rng(3)
+    for m, n, rank in [(40, 40, None), (55, 30, None), (48, 48, 7)]:
+        a = rng.standard_normal((m, n)) if rank is None else rng.standard_normal((m, rank)) @ rng.standard_normal((rank, n))
+        U, s, V = P.svd_via_gk(a, smax=8)
+        ref = np.linalg.svd(a, compute_uv=False)
+        r = int(np.sum(ref > 1e-12 * ref[0]))
+        assert np.abs(s - ref).max() < 1e-13 * ref[0]
+        assert np.abs((U * s) @ V.T - a).max() < 1e-13 * ref[0]
+        assert np.abs(U[:, :r].T @ U[:, :r] - np.eye(r)).max() < 1e-10
