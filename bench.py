@@ -311,7 +311,7 @@ def run_ours(args):
                         "gemm_dmma_kernel (einsum contractions, trailing updates, back-transform, D&C merges) on 4096^3":
                             {"achieved_tflops": gemm_tf, "peak_tflops": dmma_peak, "frac": gemm_tf / dmma_peak if dmma_peak else None}}}
         # -- CPU baseline on a bounded sample (same box, same run)
-        if args.no_cpu_baseline:
+        if args.no_cpu_baseline or world > 1:      # the CPU baseline is measured on rank 0 at N = 1 only
             cpu = None
         else:
             cdt, cns, _ = cpu_reference_sample(args.ref_maxit)
