@@ -19,7 +19,8 @@
  *     context are serialised by the caller; different contexts are independent.
  *     Results are valid on return (synchronous semantics).
  *   - Tapes are opaque, created by a forward call, consumed by any number of
- *     backward calls, released with tnad_tape_free.
+ *     backward calls, released with tnad_tape_free.  A tape belongs to its context:
+ *     tnad_destroy fails (TNAD_ERR_ARG) while tapes of the context are alive.
  *   - There is no CPU fallback: without a usable sm_100 device tnad_create fails.
  */
 #ifndef TNAD_H
@@ -59,6 +60,9 @@ TNAD_API int tnad_create(int device, tnad_ctx** out);
 TNAD_API int tnad_destroy(tnad_ctx* ctx);
 TNAD_API const char* tnad_last_error(tnad_ctx* ctx);       /* ctx may be NULL: message of a failed tnad_create */
 TNAD_API int tnad_set_pointer_mode(tnad_ctx* ctx, int mode);
+/* A/B switches.  Every TNAD_* environment variable is read once, at tnad_create; afterwards this call
+ * changes an entry of the context's table (value == NULL removes it).  Nothing on the hot path reads the environment. */
+TNAD_API int tnad_set_option(tnad_ctx* ctx, const char* name, const char* value);
 TNAD_API int tnad_synchronize(tnad_ctx* ctx);
 /* counters: kernels launched by this library on ctx since creation / last reset */
 TNAD_API int64_t tnad_launch_count(tnad_ctx* ctx);
@@ -83,18 +87,28 @@ TNAD_API int tnad_contract(tnad_ctx* ctx, const char* spec,
 TNAD_API int tnad_contract_plan(const char* spec, const int64_t* dimsA, int rankA,
                        const int64_t* dimsB, int rankB, int64_t* plan);
 
+/* Gauge of every decomposition returned by this library (the "sign-fix"): LAPACK leaves the column signs of U to
+ * chance; here column j of U is oriented so that its largest-magnitude entry (first one on ties)
+ * is positive and column j of V follows, fused into the kernel that sorts / truncates the vectors.  lnZ, energies,
+ * magnetisation and all gradients do not depend on it; corner / edge become comparable entry by entry. */
+
 /* LinearAlgebra.svd(A) as used at trg.jl:36 and ctmrg.jl:136: thin SVD, A (m x n) = U diag(S) V^T,
  * k = min(m,n), U m x k, S k (descending), V n x k.  One-sided block Jacobi on the device. */
 TNAD_API int tnad_svd(tnad_ctx* ctx, const double* A, int m, int n, double* U, double* S, double* V,
              int* sweeps_out /* may be NULL */);
 
-/* svd of a symmetric matrix as it occurs at ctmrg.jl:135-136 (cpmat + cpmat'): two-sided block Jacobi
- * eigensolver, A = Q L Q' returned as U = Q, S = |L| (descending), V = Q sign(L).  A is symmetrised as
- * (A + A')/2. */
+/* svd of a symmetric matrix as it occurs at ctmrg.jl:135-136 (cpmat + cpmat'): A = Q L Q' returned as U = Q,
+ * S = |L| (descending), V = Q sign(L).  Solver: the direct one (two-stage tridiagonalisation, divide and conquer,
+ * back-transformation; default from n >= 48) or two-sided block Jacobi (below that; option TNAD_SYMEIG = 1 | 2 forces
+ * one).  A is symmetrised as (A + A')/2. */
 TNAD_API int tnad_svd_sym(tnad_ctx* ctx, const double* A, int n, double* U, double* S, double* V, int* sweeps_out);
 
 /* trg_svd(t, dmax, tol)  (trg.jl:33-44).  t is (d1,d2,d3,d4); u gets (d1,d2,k), v gets (k,d3,d4);
- * the buffers must hold dmax columns/rows; *k_out = kept rank. */
+ * the buffers must hold dmax columns/rows; *k_out = kept rank by the reference's rule
+ * k = min(searchsortedfirst(s, tol, rev=true), dmax, length(s)) applied to the computed spectrum.
+ * Noise floor: singular values <= 16 eps sqrt(max(m,n)) |t|_F are numerically null; LAPACK returns rounding noise
+ * there, this library returns exact zeros for them (their factor columns are zero and carry no cotangent).  The kept
+ * rank still follows the rule literally, so shapes equal the reference's for tol >= that floor. */
 TNAD_API int tnad_trg_svd(tnad_ctx* ctx, const double* t, int d1, int d2, int d3, int d4, int dmax, double tol,
                  double* u, double* v, int* k_out);
 
@@ -118,6 +132,13 @@ TNAD_API int tnad_ctmrg_init_raw(tnad_ctx* ctx, const double* bulk, int D, int c
 TNAD_API int tnad_ctmrgstep(tnad_ctx* ctx, const double* bulk, int D, int chi,
                    const double* corner_in, const double* edge_in,
                    double* corner_out, double* edge_out, double* vals);
+/* Pullback of ONE ctmrgstep (what Zygote derives from ctmrg.jl:126-153 with the rules of autodiff.jl and trg.jl:55-105):
+ * given the cotangents of the step's outputs returns those of bulk (D^4, required), corner_in and edge_in (optional).
+ * The forward step is recomputed internally. */
+TNAD_API int tnad_ctmrgstep_backward(tnad_ctx* ctx, const double* bulk, int D, int chi,
+                            const double* corner_in, const double* edge_in,
+                            const double* dcorner_out, const double* dedge_out,
+                            double* dbulk, double* dcorner_in, double* dedge_in);
 /* ctmrg(rt; tol, maxit) with the reference stop rule (counter from -1). corner/edge are in/out.
  * steps_done, vals (chi*D) and tape may be NULL. */
 TNAD_API int tnad_ctmrg(tnad_ctx* ctx, const double* bulk, int D, int chi, double* corner, double* edge,
@@ -132,6 +153,11 @@ TNAD_API int tnad_ctmrg_backward(tnad_ctx* ctx, tnad_tape* tape, const double* d
 /* expectationvalue(h, ap, rt): h (s,s,s,s), ap (D,D,D,D,s,s) */
 TNAD_API int tnad_expectationvalue(tnad_ctx* ctx, const double* h, const double* ap, int D, int s,
                           const double* corner, const double* edge, int chi, double* e);
+/* pullback of expectationvalue: cotangents of ap (D,D,D,D,s,s), corner and edge for the output cotangent ybar; any
+ * output may be NULL */
+TNAD_API int tnad_expectationvalue_backward(tnad_ctx* ctx, const double* h, const double* ap, int D, int s,
+                                   const double* corner, const double* edge, int chi, double ybar,
+                                   double* dap, double* dcorner, double* dedge);
 /* energy(h, ipeps; chi, tol, maxit) and, when gradA != NULL, its gradient w.r.t. ipeps.bulk
  * exactly as Zygote + src/autodiff.jl compute it.  A is (d,d,d,d,s). steps_done may be NULL. */
 TNAD_API int tnad_energy(tnad_ctx* ctx, const double* h, const double* A, int d, int s, int chi,
@@ -139,6 +165,20 @@ TNAD_API int tnad_energy(tnad_ctx* ctx, const double* h, const double* A, int d,
 /* magnetisation read-out (exampletensors.jl:63-68): |<env,m>/<env,a>| */
 TNAD_API int tnad_magnetisation_readout(tnad_ctx* ctx, const double* a, const double* m, int D,
                                const double* corner, const double* edge, int chi, double* mag);
+
+/* pullback of the read-out (test/ctmrg.jl:44-46 differentiates magnetisation with Zygote): cotangents of a, m,
+ * corner, edge for the output cotangent ybar; any output may be NULL.  Chained with tnad_ctmrg_backward (whose
+ * dbulk adds to da) this gives d magnetisation / d beta. */
+TNAD_API int tnad_magnetisation_backward(tnad_ctx* ctx, const double* a, const double* m, int D,
+                                const double* corner, const double* edge, int chi, double ybar,
+                                double* da, double* dm, double* dcorner, double* dedge);
+
+/* ---- multi-GPU: independent instances (beta sweeps, parameter scans; no communication) ---------------------- */
+/* ninst TRG instances (tensors: ninst arrays (d0,d1,d0,d1) back to back, HOST memory), instance i on device
+ * devices[i mod ngpu] (devices == NULL: 0..ngpu-1), one context and one host thread per device.  lnZ[ninst];
+ * grads (ninst arrays like the tensors: d lnZ / d a) may be NULL.  errbuf receives the first failure message. */
+TNAD_API int tnad_trg_sweep(const double* tensors, int ninst, int d0, int d1, int chi, int niter, double tol,
+                   int ngpu, const int* devices, double* lnZ, double* grads, char* errbuf, int errlen);
 
 /* ---- pieces used by the chi-sharded multi-GPU step (tensornetworkad.jl_b200/sharded.py) -------- */
 /* svd(A + A') for a square A (ctmrg.jl:133-135: `cpmat += adjoint(cpmat); svd(cpmat)`), same solver as tnad_svd_sym */
@@ -161,8 +201,10 @@ TNAD_API int tnad_host_free(tnad_ctx* ctx, double* hptr);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of ctx is launched on) */
 TNAD_API int tnad_timer_start(tnad_ctx* ctx);
 TNAD_API int tnad_timer_stop(tnad_ctx* ctx, double* ms);
-/* per-kernel-family device time: enable, run, then read.  families: 0 jacobi_gram, 1 jacobi_eig,
- * 2 jacobi_update, 3 gemm (contractions), 4 other.  ms[i] = summed duration, count[i] = launches. */
+/* per-kernel-family device time: enable, run, then read.  families: 0 jacobi_gram (one-sided Jacobi only),
+ * 1 eigensolver panel / chase / pivot kernels (the latency-bound kernels of whichever symmetric solver ran),
+ * 2 jacobi_update, 3 gemm (every contraction and every GEMM inside the eigensolver), 4 other.
+ * ms[i] = summed duration, count[i] = launches. */
 TNAD_API int tnad_set_kernel_timing(tnad_ctx* ctx, int enable);
 TNAD_API int tnad_kernel_timing(tnad_ctx* ctx, double* ms /* [8] */, int64_t* count /* [8] */);
 /* FP64 tensor-core (DMMA m8n8k4) issue-rate microbenchmark: register-resident operands, no memory

@@ -47,7 +47,8 @@ __all__ = [
     "svd", "trg_svd", "svd_back", "trg", "trg_value_and_grad", "trg_dbeta",
     "init_raw", "init_random", "ctmrgstep", "ctmrgstep_literal", "ctmrg", "ctmrg_backward",
     "indexperm_symmetrize", "double_layer", "expectationvalue", "energy", "energy_value_and_grad",
-    "magnetisation_readout", "magnetisation", "num_grad",
+    "magnetisation_readout", "magnetisation", "num_grad", "canonical_gauge", "magnetisation_readout_back",
+    "magnetisation_value_and_dbeta", "dmag_tensor_ising",
 ]
 
 ISING_BETA_C = math.log(1 + math.sqrt(2)) / 2  # exampletensors.jl:2
@@ -172,6 +173,17 @@ def svd(A, driver="gesdd"):
     """LinearAlgebra.svd: thin SVD, returns U, S, V with A = U diag(S) V^H (LAPACK gesdd)."""
     U, S, Vh = sla.svd(A, full_matrices=False, lapack_driver=driver)
     return U, S, Vh.conj().T
+
+
+def canonical_gauge(U, V=None):
+    """Canonical column signs: the largest-magnitude entry of every column of U
+    (first one on ties) is made positive; V, when given, follows column by column so U diag(S) V^H is unchanged.
+    Not part of the reference (its gauge is whatever LAPACK returns); used by the tests so that gauge-dependent
+    tensors (corner, edge, U itself) of two implementations can be compared entry by entry."""
+    idx = np.argmax(np.abs(U), axis=0)
+    sg = np.sign(U[idx, np.arange(U.shape[1])])
+    sg = np.where(sg == 0, 1.0, sg)
+    return (U * sg[None, :], None if V is None else V * sg[None, :])
 
 
 def rank_rule(S, dmax, tol):
@@ -358,8 +370,9 @@ def ctmrgstep_literal(bulk, corner, edge, driver="gesdd"):
     return corner, edge, vals
 
 
-def ctmrgstep(bulk, corner, edge, driver="gesdd", tape=None):
-    """ctmrg.jl:126-153 in the optimal pairwise order, never materialising `tp`."""
+def ctmrgstep(bulk, corner, edge, driver="gesdd", tape=None, signfix=False):
+    """ctmrg.jl:126-153 in the optimal pairwise order, never materialising `tp`.
+    signfix=True puts U into the canonical gauge (canonical_gauge) before the projection."""
     D, chi = bulk.shape[0], corner.shape[0]
     n = chi * D
     X1 = es("iba,ad->ibd", edge, corner)
@@ -368,6 +381,8 @@ def ctmrgstep(bulk, corner, edge, driver="gesdd", tape=None):
     CP = rsh(cp, (n, n))
     M = CP + CP.T
     U, S, V = svd(M, driver)
+    if signfix:
+        U, V = canonical_gauge(U, V)
     Z = U[:, :chi]
     z = rsh(Z, (chi, D, chi))
     W = CP @ Z
@@ -589,6 +604,60 @@ def magnetisation_readout(a, m, corner, edge):
     mag = np.sum(env * m)
     nrm = np.sum(env * a)
     return abs(mag / nrm)
+
+
+def magnetisation_readout_back(a, m, corner, edge, ybar=1.0):
+    """Reverse of magnetisation_readout (exampletensors.jl:63-68 under Zygote): cotangents of
+    (a, m, corner, edge) for y = |mag/norm|."""
+    ct = es("ia,ajb->ijb", corner, edge)
+    ctc = es("ijb,bk->ijk", ct, corner)
+    e1 = es("alc,ckd->alkd", ctc, edge)
+    e2 = es("bjd,bia->jdia", ctc, edge)
+    env = es("alkd,jdia->ijkl", e1, e2)
+    mag, nrm = np.sum(env * m), np.sum(env * a)
+    r = mag / nrm
+    sg = 1.0 if r >= 0 else -1.0
+    magbar, nrmbar = ybar * sg / nrm, -ybar * sg * mag / nrm ** 2
+    envbar = magbar * m + nrmbar * a
+    abar, mbar = nrmbar * env, magbar * env
+    e1bar = es("ijkl,jdia->alkd", envbar, e2)
+    e2bar = es("alkd,ijkl->jdia", e1, envbar)
+    ctcbar = es("alkd,ckd->alc", e1bar, edge) + es("jdia,bia->bjd", e2bar, edge)
+    edgebar = es("alc,alkd->ckd", ctc, e1bar) + es("bjd,jdia->bia", ctc, e2bar)
+    ctbar = es("ijk,bk->ijb", ctcbar, corner)
+    cornerbar = es("ijb,ijk->bk", ct, ctcbar) + es("ijb,ajb->ia", ctbar, edge)
+    edgebar = edgebar + es("ia,ijb->ajb", corner, ctbar)
+    return abar, mbar, cornerbar, edgebar
+
+
+def dmag_tensor_ising(beta):
+    """d mag_tensor / d beta (exampletensors.jl:43-48 differentiated: product rule over the four q factors)."""
+    cb, sb = math.sqrt(math.cosh(beta)), math.sqrt(math.sinh(beta))
+    q = _ising_q(beta)
+    dcb, dsb = math.sinh(beta) / (2 * cb), math.cosh(beta) / (2 * sb)
+    dq = 1 / math.sqrt(2) * np.array([[dcb + dsb, dcb - dsb], [dcb - dsb, dcb + dsb]])
+    a = np.zeros((2, 2, 2, 2))
+    a[0, 0, 0, 0] = 1.0
+    a[1, 1, 1, 1] = -1.0
+    out = np.zeros((2, 2, 2, 2))
+    for slot in range(4):
+        qs = [q, q, q, q]
+        qs[slot] = dq
+        out += np.einsum("abcd,ai,bj,ck,dl->ijkl", a, *qs)
+    return out
+
+
+def magnetisation_value_and_dbeta(beta, chi, corner0, edge0, tol=1e-6, maxit=100):
+    """magnetisation and d/d beta as Zygote computes it at test/ctmrg.jl:44-46: the environment initialisation is
+    constant (autodiff.jl:5), the gradient flows through every ctmrgstep (bulk = a) and through the read-out."""
+    a, m = model_tensor_ising(beta), mag_tensor_ising(beta)
+    tape = []
+    corner, edge, _, _ = ctmrg(a, corner0, edge0, tol, maxit, tape=tape)
+    y = magnetisation_readout(a, m, corner, edge)
+    abar, mbar, cbar, ebar = magnetisation_readout_back(a, m, corner, edge)
+    bbar, _, _ = ctmrg_backward(a, tape, cbar, ebar)
+    abar = abar + bbar
+    return y, float(np.sum(abar * dmodel_tensor_ising(beta)) + np.sum(mbar * dmag_tensor_ising(beta)))
 
 
 def magnetisation(beta, chi, rng=None, tol=1e-6, maxit=100, env="random"):

@@ -20,7 +20,8 @@ from typing import Callable, Optional
 
 import numpy as np
 
-from ._lib import (Context, Tape, TnadError, DimensionMismatch, contract_plan, load_library, farray, SIGNATURES)
+from ._lib import (Context, Tape, TnadError, DimensionMismatch, contract_plan, load_library, farray, SIGNATURES,
+                   trg_sweep)
 
 __all__ = [
     "trg", "trg_value_and_grad", "num_grad", "ctmrg", "ctmrgstep", "optimiseipeps", "hamiltonian", "model_tensor",
@@ -28,7 +29,8 @@ __all__ = [
     "SquareCTMRGRuntime", "IPEPS", "SquareIPEPS", "energy", "energy_and_gradient", "expectationvalue",
     "magnetisation", "magofbeta", "isingbetac", "trg_svd", "svd", "svd_back", "fixedpoint", "StopFunction",
     "indexperm_symmetrize", "diaglocalhamiltonian", "tensorfromclassical", "getchi", "getD", "getd", "gets",
-    "Context", "default_context", "DimensionMismatch", "TnadError",
+    "Context", "default_context", "DimensionMismatch", "TnadError", "magnetisation_value_and_grad", "dmag_tensor",
+    "dmodel_tensor", "trg_sweep",
 ]
 
 _default_ctx: Optional[Context] = None
@@ -140,6 +142,20 @@ def mag_tensor(model: HamiltonianModel, beta: float) -> np.ndarray:
         raise TypeError("mag_tensor is defined for Ising()")
     q = _ising_q(beta)
     return np.asfortranarray(np.einsum("abcd,ai,bj,ck,dl->ijkl", _ising_core(-1.0), q, q, q, q))
+
+
+def dmag_tensor(model: HamiltonianModel, beta: float) -> np.ndarray:
+    """d mag_tensor / d beta (exampletensors.jl:43-48 differentiated by the product rule; the chain-rule factor of
+    `Zygote.gradient(beta -> magnetisation(Ising(), beta, chi), beta)`, test/ctmrg.jl:44-46)."""
+    if not isinstance(model, Ising):
+        raise TypeError("dmag_tensor is defined for Ising()")
+    q, dq = _ising_q(beta), _ising_dq(beta)
+    out = np.zeros((2, 2, 2, 2))
+    for slot in range(4):
+        qs = [q, q, q, q]
+        qs[slot] = dq
+        out += np.einsum("abcd,ai,bj,ck,dl->ijkl", _ising_core(-1.0), *qs)
+    return np.asfortranarray(out)
 
 
 def tensorfromclassical(ham) -> np.ndarray:
@@ -366,6 +382,26 @@ def magnetisation(model: HamiltonianModel, beta: float, chi: int, rng=None, tol=
     rt = SquareCTMRGRuntime(a, env, chi, rng=rng, ctx=c)
     rt = ctmrg(rt, tol, maxit, ctx=c)
     return c.magnetisation_readout(a, m, rt.corner, rt.edge)
+
+
+def magnetisation_value_and_grad(model: HamiltonianModel, beta: float, chi: int, rng=None, tol=1e-6, maxit=100,
+                                 env="random", ctx=None):
+    """magnetisation and `Zygote.gradient(beta -> magnetisation(model, beta, chi), beta)[1]` (test/ctmrg.jl:44-46).
+
+    The environment initialisation is constant under AD (autodiff.jl:5); the gradient flows through the read-out
+    (tnad_magnetisation_backward), through every executed ctmrgstep (tnad_ctmrg_backward, bulk = a) and, on the
+    host, through model_tensor / mag_tensor."""
+    c = _ctx(ctx)
+    a, m = model_tensor(model, beta), mag_tensor(model, beta)
+    rt = SquareCTMRGRuntime(a, env, chi, rng=rng, ctx=c)
+    co, ed, _, _, tape = c.ctmrg(rt.bulk, rt.corner, rt.edge, tol, maxit, want_tape=True)
+    try:
+        y = c.magnetisation_readout(a, m, co, ed)
+        da, dm, dc, de = c.magnetisation_backward(a, m, co, ed, 1.0)
+        da = da + c.ctmrg_backward(tape, dc, de)
+    finally:
+        tape.free()
+    return y, float(np.sum(da * dmodel_tensor(model, beta)) + np.sum(dm * dmag_tensor(model, beta)))
 
 
 def optimiseipeps(ipeps: IPEPS, h, chi: int, tol: float, maxit: int, optimargs: Optional[dict] = None,

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -27,6 +28,7 @@ SIGNATURES = {
     "tnad_destroy": (C.c_int, [C.c_void_p]),
     "tnad_last_error": (C.c_char_p, [C.c_void_p]),
     "tnad_set_pointer_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "tnad_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "tnad_synchronize": (C.c_int, [C.c_void_p]),
     "tnad_launch_count": (C.c_int64, [C.c_void_p]),
     "tnad_reset_launch_count": (C.c_int, [C.c_void_p]),
@@ -61,6 +63,14 @@ SIGNATURES = {
     "tnad_magnetisation_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, c_double_p]),
     "tnad_last_timing": (C.c_int, [C.c_void_p, c_double_p]),
+    "tnad_ctmrgstep_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tnad_expectationvalue_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                 C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tnad_magnetisation_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tnad_trg_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                 c_int_p, c_double_p, C.c_void_p, C.c_char_p, C.c_int]),
     "tnad_svd_symmetrized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
     "tnad_sytrd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tnad_stedc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -84,11 +94,17 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIBPATH):
-        if not build_if_missing:
-            raise OSError(f"{_LIBPATH} is missing; run `python __graft_entry__.py build`")
-        from .build import build_library
-        build_library()
+    if build_if_missing:
+        # build_library() is incremental (mtime check per source): a no-op when the .so is current, a rebuild when
+        # csrc/ was edited, an error when nvcc is missing and the .so is stale or absent
+        try:
+            from .build import build_library
+            build_library()
+        except Exception:
+            if not os.path.exists(_LIBPATH):
+                raise
+    elif not os.path.exists(_LIBPATH):
+        raise OSError(f"{_LIBPATH} is missing; run `python __graft_entry__.py build`")
     lib = C.CDLL(_LIBPATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)     # AttributeError if the symbol is not exported
@@ -132,9 +148,16 @@ class Context:
             raise TnadError(rc, msg.decode() if msg else "")
         self.h = h
         self.device = device
+        self._tapes = weakref.WeakSet()
+
+    def set_option(self, name: str, value=None):
+        """A/B switch of this context (tnad_set_option); value None removes the entry."""
+        self.check(self.lib.tnad_set_option(self.h, name.encode(), None if value is None else str(value).encode()))
 
     def close(self):
         if getattr(self, "h", None):
+            for t in list(getattr(self, "_tapes", [])):     # tapes own device buffers of this context: free them first
+                t.free()
             for p in getattr(self, "_pinned", []):
                 self.lib.tnad_host_free(self.h, C.c_void_p(p))
             self._pinned = []
@@ -182,7 +205,7 @@ class Context:
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()
         self.check(self.lib.tnad_kernel_timing(self.h, ms, cnt))
-        names = ["m_update", "pivot_eig", "q_update", "gemm", "other"]
+        names = ["m_update", "eig_panel", "q_update", "gemm", "other"]
         out = {n: dict(ms=ms[i], launches=int(cnt[i])) for i, n in enumerate(names)}
         out["m_update"]["blocks"] = int(cnt[5])     # executed 64x64 two-sided block updates (2 x 2*64^3 flop each)
         out["q_update"]["slabs"] = int(cnt[6])      # executed 128x64 panel rotations (2*128*64*64 flop each)
@@ -350,7 +373,27 @@ class Context:
         self.check(self.lib.tnad_ctmrg_backward(self.h, tape.h, _p(dcorner), _p(dedge), _p(db), _p(dc0), _p(de0)))
         return (db, dc0, de0) if want_init else db
 
+    def ctmrgstep_backward(self, bulk, corner, edge, dcorner_out, dedge_out):
+        """Pullback of one ctmrgstep: (dbulk, dcorner_in, dedge_in)."""
+        bulk = farray(bulk)
+        D, chi = bulk.shape[0], np.shape(corner)[0]
+        corner, edge = farray(corner, (chi, chi)), farray(edge, (chi, D, chi))
+        dco, deo = farray(dcorner_out, (chi, chi)), farray(dedge_out, (chi, D, chi))
+        db = np.empty((D, D, D, D), order="F"); dc = np.empty((chi, chi), order="F"); de = np.empty((chi, D, chi), order="F")
+        self.check(self.lib.tnad_ctmrgstep_backward(self.h, _p(bulk), D, chi, _p(corner), _p(edge), _p(dco), _p(deo),
+                                                    _p(db), _p(dc), _p(de)))
+        return db, dc, de
+
     # ---- energy --------------------------------------------------------------------------------------
+    def expectationvalue_backward(self, h, ap, corner, edge, ybar=1.0):
+        h, ap = farray(h), farray(ap)
+        s, D, chi = h.shape[0], ap.shape[0], np.shape(corner)[0]
+        corner, edge = farray(corner, (chi, chi)), farray(edge, (chi, D, chi))
+        dap = np.empty(ap.shape, order="F"); dc = np.empty((chi, chi), order="F"); de = np.empty((chi, D, chi), order="F")
+        self.check(self.lib.tnad_expectationvalue_backward(self.h, _p(h), _p(ap), D, s, _p(corner), _p(edge), chi,
+                                                           float(ybar), _p(dap), _p(dc), _p(de)))
+        return dap, dc, de
+
     def expectationvalue(self, h, ap, corner, edge):
         h, ap = farray(h), farray(ap)
         s, D, chi = h.shape[0], ap.shape[0], np.shape(corner)[0]
@@ -436,11 +479,33 @@ class Context:
         return mag.value
 
 
+def trg_sweep(tensors, chi, niter, tol=1e-16, ngpu=1, devices=None, grad=False):
+    """tnad_trg_sweep: independent TRG instances fanned out over `ngpu` devices inside the library (one context and
+    one host thread per device).  tensors: (ninst, d0, d1, d0, d1).  Returns lnZ (ninst) [, grads like tensors]."""
+    lib = load_library()
+    ts = [farray(t) for t in tensors]
+    ninst = len(ts)
+    d0, d1 = ts[0].shape[0], ts[0].shape[1]
+    flat = np.concatenate([t.ravel(order="F") for t in ts]) if ninst else np.zeros(0)
+    lnz = np.zeros(ninst)
+    g = np.zeros(flat.size) if grad else None
+    dev = (C.c_int * ngpu)(*devices) if devices is not None else None
+    err = C.create_string_buffer(512)
+    rc = lib.tnad_trg_sweep(_p(flat), ninst, d0, d1, int(chi), int(niter), float(tol), int(ngpu), dev,
+                            lnz.ctypes.data_as(c_double_p), _p(g), err, 512)
+    if rc != 0:
+        raise TnadError(rc, err.value.decode())
+    if grad:
+        return lnz, [np.reshape(g[i * ts[0].size:(i + 1) * ts[0].size], ts[0].shape, order="F") for i in range(ninst)]
+    return lnz
+
+
 class Tape:
     """Opaque device-resident record of a forward pass (tnad_tape)."""
 
     def __init__(self, ctx: Context, h, shape):
         self.ctx, self.h, self.shape = ctx, h, tuple(shape)
+        ctx._tapes.add(self)
 
     def free(self):
         if self.h:

@@ -3,6 +3,10 @@
 #include "eigdc.h"
 #include <algorithm>
 #include <mutex>
+#include <thread>
+
+#include <unistd.h>
+extern char** environ;
 
 using namespace tnad;
 
@@ -54,6 +58,10 @@ int tnad_create(int device, tnad_ctx** out) {
     c = new tnad_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    TNAD_CUDA(cudaDeviceGetAttribute(&c->coop_launch, cudaDevAttrCooperativeLaunch, device));
+    for (char** e = environ; e && *e; ++e)     // A/B switches: read the environment once, here
+      if (strncmp(*e, "TNAD_", 5) == 0)
+        if (const char* eq = strchr(*e, '=')) c->opts[std::string(*e, eq - *e)] = std::string(eq + 1);
     // the main stream carries the latency-critical pivot kernels of the eigensolver: give it the highest
     // priority so its CTAs are scheduled ahead of the bulk update kernels running on streams 2 and 3
     int prio_lo = 0, prio_hi = 0;
@@ -88,6 +96,10 @@ int tnad_create(int device, tnad_ctx** out) {
 
 int tnad_destroy(tnad_ctx* c) {
   if (!c) return TNAD_OK;
+  if (c->live_tapes > 0) {   // a tape owns device buffers that are released on this context's stream
+    c->err = "tnad_destroy: " + std::to_string(c->live_tapes) + " tape(s) of this context are still alive; call tnad_tape_free first";
+    return TNAD_ERR_ARG;
+  }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->stream2) cudaStreamSynchronize(c->stream2);
@@ -114,6 +126,13 @@ int tnad_destroy(tnad_ctx* c) {
   if (c->stream3) cudaStreamDestroy(c->stream3);
   cudaStreamDestroy(c->stream);
   delete c;
+  return TNAD_OK;
+}
+
+int tnad_set_option(tnad_ctx* c, const char* name, const char* value) {
+  if (!c || !name) return TNAD_ERR_ARG;
+  if (value) c->opts[name] = value;
+  else c->opts.erase(name);
   return TNAD_OK;
 }
 
@@ -326,11 +345,13 @@ int tnad_trg_forward(tnad_ctx* c, const double* a, int d0, int d1, int chi, int 
     tp = new tnad_tape();
     tp->ctx = c;
     tp->kind = 1;
+    c->live_tapes++;
   }
   try {
     Span sp(c, 0);
     *lnZ = trg_forward(c, ta, chi, niter, tol, tp ? &tp->trg : nullptr);
   } catch (...) {
+    if (tp) c->live_tapes--;
     delete tp;
     throw;
   }
@@ -355,8 +376,10 @@ int tnad_trg_backward(tnad_ctx* c, tnad_tape* tape, double dlnZ, double* da) {
 
 int tnad_tape_free(tnad_tape* tape) {
   if (!tape) return TNAD_OK;
-  if (tape->ctx) cudaSetDevice(tape->ctx->device);
+  tnad_ctx* c = tape->ctx;
+  if (c) cudaSetDevice(c->device);
   delete tape;
+  if (c) c->live_tapes--;
   return TNAD_OK;
 }
 
@@ -386,6 +409,25 @@ int tnad_ctmrgstep(tnad_ctx* c, const double* bulk, int D, int chi, const double
   TNAD_API_END(c)
 }
 
+int tnad_ctmrgstep_backward(tnad_ctx* c, const double* bulk, int D, int chi, const double* corner_in,
+                            const double* edge_in, const double* dcorner_out, const double* dedge_out, double* dbulk,
+                            double* dcorner_in, double* dedge_in) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && chi >= 1 && dcorner_out && dedge_out && dbulk, "tnad_ctmrgstep_backward: bad arguments");
+  Tens b = t_in(c, bulk, {D, D, D, D}), co = t_in(c, corner_in, {chi, chi}), ed = t_in(c, edge_in, {chi, D, chi});
+  Tens cb3 = t_in(c, dcorner_out, {chi, chi}), eb3 = t_in(c, dedge_out, {chi, D, chi});
+  Tens cn, en, cb, eb;
+  std::vector<double> v;
+  CtmrgStepRec rec;
+  ctmrg_step(c, b, co, ed, cn, en, v, &rec);   // forward with a record (the pullback of one step is self-contained)
+  Tens bb = t_alloc(c, {D, D, D, D}, true);
+  ctmrg_step_backward(c, b, rec, cb3, eb3, bb, cb, eb, 1e-40);
+  t_out(c, bb, dbulk);
+  if (dcorner_in) t_out(c, cb, dcorner_in);
+  if (dedge_in) t_out(c, eb, dedge_in);
+  TNAD_API_END(c)
+}
+
 int tnad_ctmrg(tnad_ctx* c, const double* bulk, int D, int chi, double* corner, double* edge, double tol, int maxit,
                int* steps_done, double* vals, tnad_tape** tape) {
   TNAD_API_BEGIN(c)
@@ -400,6 +442,7 @@ int tnad_ctmrg(tnad_ctx* c, const double* bulk, int D, int chi, double* corner, 
     tp = new tnad_tape();
     tp->ctx = c;
     tp->kind = 2;
+    c->live_tapes++;
   }
   std::vector<double> v;
   int ns = 0;
@@ -407,6 +450,7 @@ int tnad_ctmrg(tnad_ctx* c, const double* bulk, int D, int chi, double* corner, 
     Span sp(c, 0);
     ns = ctmrg_loop(c, b, co, ed, tol, maxit, v, tp ? &tp->ctmrg : nullptr);
   } catch (...) {
+    if (tp) c->live_tapes--;
     delete tp;
     throw;
   }
@@ -488,6 +532,23 @@ int tnad_expectationvalue(tnad_ctx* c, const double* h, const double* ap, int D,
   TNAD_API_END(c)
 }
 
+int tnad_expectationvalue_backward(tnad_ctx* c, const double* h, const double* ap, int D, int s, const double* corner,
+                                   const double* edge, int chi, double ybar, double* dap, double* dcorner,
+                                   double* dedge) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && s >= 1 && chi >= 1, "tnad_expectationvalue_backward: bad arguments");
+  Tens th = t_in(c, h, {s, s, s, s}), tap = t_in(c, ap, {D, D, D, D, s, s});
+  Tens co = t_in(c, corner, {chi, chi}), ed = t_in(c, edge, {chi, D, chi});
+  ExpvalTape et;
+  expectationvalue(c, th, tap, co, ed, &et);
+  Tens apbar, cbar, ebar;
+  expectationvalue_back(c, co, ed, et, ybar, apbar, cbar, ebar);
+  if (dap) t_out(c, apbar, dap);
+  if (dcorner) t_out(c, cbar, dcorner);
+  if (dedge) t_out(c, ebar, dedge);
+  TNAD_API_END(c)
+}
+
 int tnad_energy(tnad_ctx* c, const double* h, const double* A, int d, int s, int chi, double tol, int maxit,
                 double* e, double* gradA, int* steps_done) {
   TNAD_API_BEGIN(c)
@@ -512,6 +573,67 @@ int tnad_magnetisation_readout(tnad_ctx* c, const double* a, const double* m, in
   Tens co = t_in(c, corner, {chi, chi}), ed = t_in(c, edge, {chi, D, chi});
   *mag = magnetisation_readout(c, ta, tm, co, ed);
   TNAD_API_END(c)
+}
+
+int tnad_magnetisation_backward(tnad_ctx* c, const double* a, const double* m, int D, const double* corner,
+                                const double* edge, int chi, double ybar, double* da, double* dm, double* dcorner,
+                                double* dedge) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && chi >= 1, "tnad_magnetisation_backward: bad arguments");
+  Tens ta = t_in(c, a, {D, D, D, D}), tm = t_in(c, m, {D, D, D, D});
+  Tens co = t_in(c, corner, {chi, chi}), ed = t_in(c, edge, {chi, D, chi});
+  MagTape mt;
+  magnetisation_readout(c, ta, tm, co, ed, &mt);
+  Tens ab, mb, cb, eb;
+  magnetisation_readout_back(c, ta, tm, co, ed, mt, ybar, ab, mb, cb, eb);
+  if (da) t_out(c, ab, da);
+  if (dm) t_out(c, mb, dm);
+  if (dcorner) t_out(c, cb, dcorner);
+  if (dedge) t_out(c, eb, dedge);
+  TNAD_API_END(c)
+}
+
+// ---- multi-GPU: independent instances (beta sweeps / parameter scans, no communication) -----------------
+int tnad_trg_sweep(const double* tensors, int ninst, int d0, int d1, int chi, int niter, double tol, int ngpu,
+                   const int* devices, double* lnZ, double* grads, char* errbuf, int errlen) {
+  if (!tensors || !lnZ || ninst < 0 || d0 < 1 || d1 < 1 || ngpu < 1) return TNAD_ERR_ARG;
+  const int64_t numel = (int64_t)d0 * d1 * d0 * d1;
+  std::vector<int> rc((size_t)ngpu, TNAD_OK);
+  std::vector<std::string> msg((size_t)ngpu);
+  auto worker = [&](int g) {
+    tnad_ctx* ctx = nullptr;
+    int r = tnad_create(devices ? devices[g] : g, &ctx);
+    if (r != TNAD_OK) {
+      rc[(size_t)g] = r;
+      msg[(size_t)g] = tnad_last_error(nullptr);
+      return;
+    }
+    for (int i = g; i < ninst && r == TNAD_OK; i += ngpu) {   // instance i -> device i mod ngpu
+      tnad_tape* tape = nullptr;
+      r = tnad_trg_forward(ctx, tensors + (int64_t)i * numel, d0, d1, chi, niter, tol, lnZ + i, grads ? &tape : nullptr);
+      if (r == TNAD_OK && grads) r = tnad_trg_backward(ctx, tape, 1.0, grads + (int64_t)i * numel);
+      tnad_tape_free(tape);
+    }
+    if (r != TNAD_OK) {
+      rc[(size_t)g] = r;
+      msg[(size_t)g] = tnad_last_error(ctx);
+    }
+    tnad_destroy(ctx);
+  };
+  try {
+    std::vector<std::thread> th;
+    for (int g = 1; g < ngpu; ++g) th.emplace_back(worker, g);
+    worker(0);
+    for (auto& t : th) t.join();
+  } catch (...) {
+    return TNAD_ERR_INTERNAL;
+  }
+  for (int g = 0; g < ngpu; ++g)
+    if (rc[(size_t)g] != TNAD_OK) {
+      if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "device slot %d: %s", g, msg[(size_t)g].c_str());
+      return rc[(size_t)g];
+    }
+  return TNAD_OK;
 }
 
 }  // extern "C"

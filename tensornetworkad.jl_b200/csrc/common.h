@@ -9,6 +9,8 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <map>
+#include <atomic>
 #include <initializer_list>
 #include "../../include/tnad.h"
 
@@ -36,6 +38,38 @@ struct Error {
     if (!(cond)) ::tnad::fail(TNAD_ERR_ARG, std::string(msg));   \
   } while (0)
 
+#ifdef __CUDACC__
+// sign (+1 / -1) that makes the largest-magnitude entry of x[0:n] (first index on ties) positive; whole CTA, blockDim.x
+// a multiple of 32 and <= 1024; sh: 66 doubles of shared memory
+__device__ __forceinline__ double block_canonical_sign(const double* __restrict__ x, long long n, double* sh) {
+  double best = -1.0, val = 1.0;
+  long long bi = n;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = x[i], a = fabs(v);
+    if (a > best) { best = a; val = v; bi = i; }     // strided scan: the first index of a tie within a thread wins
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_down_sync(0xffffffffu, best, o), ov = __shfl_down_sync(0xffffffffu, val, o);
+    const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; val = ov; bi = oi; }
+  }
+  long long* shi = reinterpret_cast<long long*>(sh + 33);
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = val; shi[threadIdx.x >> 5] = bi; sh[66 + (threadIdx.x >> 5)] = best; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 1; w < nw; ++w)
+      if (sh[66 + w] > best || (sh[66 + w] == best && shi[w] < bi)) { best = sh[66 + w]; val = sh[w]; bi = shi[w]; }
+    sh[32] = val < 0.0 ? -1.0 : 1.0;
+  }
+  __syncthreads();
+  const double s = sh[32];
+  __syncthreads();
+  return s;
+}
+constexpr int SIGNFIX_SH = 100;   // doubles of shared memory block_canonical_sign needs
+#endif
+
 }  // namespace tnad
 
 struct tnad_ctx {
@@ -52,6 +86,11 @@ struct tnad_ctx {
   double* partial = nullptr;   // reduction partials (PARTIAL_SLOTS doubles)
   double* hpin = nullptr;      // pinned host staging (HPIN_SLOTS doubles)
   int num_sms = 148;
+  int coop_launch = 0;         // cudaDevAttrCooperativeLaunch, queried once at tnad_create
+  // A/B switches: every TNAD_* environment variable is read ONCE at tnad_create into this table; tnad_set_option
+  // changes an entry afterwards.  Nothing on the hot path calls getenv.
+  std::map<std::string, std::string> opts;
+  int live_tapes = 0;          // tapes created on this context and not yet freed (tnad_destroy refuses while > 0)
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // accumulators for the timing breakdown (host wall clock around synchronised phases is not
@@ -219,6 +258,14 @@ void trg_factor_back(tnad_ctx* c, int64_t m, int64_t n, int64_t k, const double*
 void add_diag_trace_back(tnad_ctx* c, Tens& abar, double w);   // abar[i,j,i,j] += w
 void trg_maxval_back(tnad_ctx* c, const Tens& da, const Tens& a_in, double maxval, double coef, Tens& da_in);
 void fill(tnad_ctx* c, double* p, int64_t n, double v);
+// option table of the context (see tnad_ctx::opts)
+const char* opt_s(const tnad_ctx* c, const char* name);                  // nullptr when unset
+int opt_i(const tnad_ctx* c, const char* name, int dflt);
+double opt_d(const tnad_ctx* c, const char* name, double dflt);
+// Canonical gauge of a decomposition (the "sign-fix" of SURVEY appendix A.10): every column j < ncols of U (m rows) is
+// multiplied by the sign that makes its largest-magnitude entry (first one on ties) positive; the same sign is applied
+// to column j of V (nv rows; V may be null).  U diag(S) V' is unchanged.
+void signfix_cols(tnad_ctx* c, double* U, int64_t ldu, int64_t m, double* V, int64_t ldv, int64_t nv, int64_t ncols);
 
 // --------------------------------------------------------------------------------------------
 // Jacobi SVD (jacobi.cu)

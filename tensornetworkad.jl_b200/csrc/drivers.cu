@@ -101,9 +101,8 @@ TrgSplit trg_split(tnad_ctx* c, const Tens& t4, int64_t dmax, double tol) {
     // from order m + n >= 96 on: Jordan-Wielandt embedding + the direct symmetric eigensolver (TNAD_TRG_SVD=jacobi
     // forces the one-sided block Jacobi path)
     const int64_t mm = t4.dim[0] * t4.dim[1], nn = t4.dim[2] * t4.dim[3];
-    const char* ev = getenv("TNAD_TRG_SVD");
-    int coop = 0;
-    TNAD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    const char* ev = opt_s(c, "TNAD_TRG_SVD");
+    const int coop = c->coop_launch;
     const bool jac = (ev && ev[0] == 'j') || mm + nn < 96 || !coop;
     sp.svd = jac ? svd_jacobi(c, t4, false, nullptr, /*complete_null=*/false) : svd_general_dc(c, t4);
   }
@@ -248,7 +247,7 @@ void ctmrg_step(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& e
   {
     Span s(c, 1);
     // svd(cpmat + cpmat') (ctmrg.jl:134-136); warm-started from the previous step's right vectors
-    const char* se = getenv("TNAD_SYMEIG");
+    const char* se = opt_s(c, "TNAD_SYMEIG");
     if (se && se[0] == '0') {
       svd = svd_jacobi(c, CP, true, (Vwarm && Vwarm->p) ? Vwarm : nullptr);   // one-sided path (A/B switch)
       if (Vwarm) *Vwarm = svd.V;
@@ -314,7 +313,7 @@ int ctmrg_loop(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge, double t
   const size_t n = (size_t)(chi * D);
   std::vector<double> oldvals(n, INFINITY);
   vals.assign(n, INFINITY);
-  const char* wenv = getenv("TNAD_WARMSTART");
+  const char* wenv = opt_s(c, "TNAD_WARMSTART");
   const bool warm = (wenv && wenv[0] == '1');   // measured: no gain on the two-sided path (cluster-limited sweeps)
   Tens Vwarm;
   long long counter = -1;   // ctmrg.jl:114
@@ -422,11 +421,8 @@ double expectationvalue(tnad_ctx* c, const Tens& h, const Tens& ap, const Tens& 
   Tens l = contract_new(c, "iejflm,efk->ijklm", Y, CTr);
   // e = <l, l, h>, n = <tr l, tr l>   (variationalipeps.jl:53-54)
   Tens lh = contract_new(c, "abckl,ijkl->abcij", l, h);
-  std::vector<double> eyeh((size_t)(s * s), 0.0);
-  for (int64_t i = 0; i < s; ++i) eyeh[(size_t)(i + s * i)] = 1.0;
-  Tens eye = t_alloc(c, {s, s});
-  h2d(c, eye.p, eyeh.data(), eyeh.size());
-  sync(c);
+  Tens eye = t_alloc(c, {s, s}, true);
+  set_identity(c, eye.p, s, s);
   Tens tl = contract_new(c, "abcij,ij->abc", l, eye);
   double* sc = c->scal + 40;
   reduce(c, RED_DOT, l, &lh, sc);
@@ -458,11 +454,8 @@ void expectationvalue_back(tnad_ctx* c, const Tens& corner, const Tens& edge, co
   Tens hs = t_clone(c, t.h);
   tcopy(c, t_perm(t.h, {2, 3, 0, 1}), hs, 1.0, 1.0);
   Tens lbar = contract_new(c, "abckl,ijkl->abcij", t.l, hs, ebar);
-  std::vector<double> eyeh((size_t)(s * s), 0.0);
-  for (int64_t i = 0; i < s; ++i) eyeh[(size_t)(i + s * i)] = 1.0;
-  Tens eye = t_alloc(c, {s, s});
-  h2d(c, eye.p, eyeh.data(), eyeh.size());
-  sync(c);
+  Tens eye = t_alloc(c, {s, s}, true);
+  set_identity(c, eye.p, s, s);
   contract(c, "abc,ij->abcij", t.tl, eye, lbar, 2.0 * nbar, 1.0);
   Tens Ybar = contract_new(c, "ijklm,efk->iejflm", lbar, t.CTr);
   Tens CTrbar = contract_new(c, "iejflm,ijklm->efk", t.Y, lbar);
@@ -514,7 +507,8 @@ double energy(tnad_ctx* c, const Tens& h, const Tens& A, int chi, double tol, in
   return y;
 }
 
-double magnetisation_readout(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge) {
+double magnetisation_readout(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge,
+                             MagTape* tape) {
   // exampletensors.jl:63-68
   Tens ct = contract_new(c, "ia,ajb->ijb", corner, edge);
   Tens ctc = contract_new(c, "ijb,bk->ijk", ct, corner);
@@ -526,7 +520,36 @@ double magnetisation_readout(tnad_ctx* c, const Tens& a, const Tens& m, const Te
   reduce(c, RED_DOT, env, &a, sc + 1);
   double v[2];
   d2h(c, v, sc, 2);
+  if (tape) {
+    tape->ct = ct; tape->ctc = ctc; tape->e1 = e1; tape->e2 = e2; tape->env = env;
+    tape->mag = v[0]; tape->nrm = v[1];
+  }
   return std::fabs(v[0] / v[1]);
+}
+
+// Reverse of the read-out as Zygote derives it (test/ctmrg.jl:44-46 differentiates magnetisation): y = |mag/norm|.
+void magnetisation_readout_back(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge,
+                                const MagTape& t, double ybar, Tens& abar, Tens& mbar, Tens& cornerbar, Tens& edgebar) {
+  const double sg = (t.mag / t.nrm) >= 0.0 ? 1.0 : -1.0;
+  const double magbar = ybar * sg / t.nrm, nrmbar = -ybar * sg * t.mag / (t.nrm * t.nrm);
+  const std::vector<int64_t> d4(a.dim, a.dim + 4);
+  Tens envbar = t_alloc_v(c, d4);
+  tcopy(c, m, envbar, magbar, 0.0);
+  tcopy(c, a, envbar, nrmbar, 1.0);
+  abar = t_alloc_v(c, d4);
+  mbar = t_alloc_v(c, d4);
+  tcopy(c, t.env, abar, nrmbar, 0.0);
+  tcopy(c, t.env, mbar, magbar, 0.0);
+  Tens e1bar = contract_new(c, "ijkl,jdia->alkd", envbar, t.e2);
+  Tens e2bar = contract_new(c, "alkd,ijkl->jdia", t.e1, envbar);
+  Tens ctcbar = contract_new(c, "alkd,ckd->alc", e1bar, edge);
+  contract(c, "jdia,bia->bjd", e2bar, edge, ctcbar, 1.0, 1.0);
+  edgebar = contract_new(c, "alc,alkd->ckd", t.ctc, e1bar);
+  contract(c, "bjd,jdia->bia", t.ctc, e2bar, edgebar, 1.0, 1.0);
+  Tens ctbar = contract_new(c, "ijk,bk->ijb", ctcbar, corner);
+  cornerbar = contract_new(c, "ijb,ijk->bk", t.ct, ctcbar);
+  contract(c, "ijb,ajb->ia", ctbar, edge, cornerbar, 1.0, 1.0);
+  contract(c, "ia,ijb->ajb", corner, ctbar, edgebar, 1.0, 1.0);
 }
 
 }  // namespace tnad

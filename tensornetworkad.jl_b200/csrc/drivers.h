@@ -69,7 +69,14 @@ double expectationvalue(tnad_ctx* c, const Tens& h, const Tens& ap, const Tens& 
 void expectationvalue_back(tnad_ctx* c, const Tens& corner, const Tens& edge, const ExpvalTape& t, double ybar,
                            Tens& apbar, Tens& cornerbar, Tens& edgebar);
 double energy(tnad_ctx* c, const Tens& h, const Tens& A, int chi, double tol, int maxit, Tens* gradA, int* steps);
-double magnetisation_readout(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge);
+struct MagTape {
+  Tens ct, ctc, e1, e2, env;
+  double mag = 0.0, nrm = 1.0;
+};
+double magnetisation_readout(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge,
+                             MagTape* tape = nullptr);
+void magnetisation_readout_back(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge,
+                                const MagTape& t, double ybar, Tens& abar, Tens& mbar, Tens& cornerbar, Tens& edgebar);
 
 }  // namespace tnad
 

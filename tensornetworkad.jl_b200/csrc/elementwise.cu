@@ -383,6 +383,25 @@ void tcopy(tnad_ctx* c, const Tens& in, Tens& out, double alpha, double beta) {
   LAUNCH_CHECK(c);
 }
 
+__global__ void k_signfix_cols(double* U, long long ldu, long long m, double* V, long long ldv, long long nv) {
+  __shared__ double sh[SIGNFIX_SH];
+  double* u = U + (long long)blockIdx.x * ldu;
+  const double s = block_canonical_sign(u, m, sh);
+  if (s < 0.0) {
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) u[i] = -u[i];
+    if (V) {
+      double* v = V + (long long)blockIdx.x * ldv;
+      for (long long i = threadIdx.x; i < nv; i += blockDim.x) v[i] = -v[i];
+    }
+  }
+}
+
+void signfix_cols(tnad_ctx* c, double* U, int64_t ldu, int64_t m, double* V, int64_t ldv, int64_t nv, int64_t ncols) {
+  if (ncols <= 0 || m <= 0) return;
+  k_signfix_cols<<<(int)ncols, 128, 0, c->stream>>>(U, ldu, m, V, ldv, nv);
+  LAUNCH_CHECK(c);
+}
+
 void fill(tnad_ctx* c, double* p, int64_t n, double v) {
   if (n <= 0) return;
   k_fill<<<grid_for(n, 4), TB, 0, c->stream>>>(p, n, v);

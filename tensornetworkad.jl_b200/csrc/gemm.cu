@@ -317,12 +317,12 @@ void launch_cfg(tnad_ctx* c, const GemmDesc& d) {
   constexpr int B_ELEMS = BKF ? BN * (BK + 4) : BK * (BN + 4);
   const size_t smem = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double) +
                       (BM + BN + 2 * STAGES * BK) * sizeof(long long);
-  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
-  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
+  static std::atomic<unsigned long long> attr_devs{0};   // kernel attributes are per device: one bit per device id (set after the attribute call: a racing thread at worst repeats it)
+  const bool attr_set = (attr_devs.load(std::memory_order_acquire) >> (c->device & 63)) & 1ULL;
   auto kern = gemm_dmma_kernel<BM, BN, WM, WN, AKF, BKF>;
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_devs |= 1ULL << (c->device & 63);
+    attr_devs.fetch_or(1ULL << (c->device & 63), std::memory_order_release);
   }
   const int S = d.splitk > 1 ? d.splitk : 1;
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.batch * S);
@@ -359,10 +359,7 @@ void gemm_run(tnad_ctx* c, const GemmDesc& d0) {
   {
     // short-K products with few 128x128 tiles (trailing updates of the tridiagonalisation, compact-WY updates): the
     // 64x64 tiling gives 4x the CTAs for the same bytes; A/B knob TNAD_GEMM_SMALLK=<K limit> (0 = off)
-    static const int smallk = [] {
-      const char* v = getenv("TNAD_GEMM_SMALLK");
-      return v ? atoi(v) : 128;   // measured at n = 2048: trailing updates 3.3 -> 2.3 ms, back-transform 2.5 -> 2.2 ms per decomposition
-    }();
+    const int smallk = opt_i(c, "TNAD_GEMM_SMALLK", 128);   // measured at n = 2048: trailing updates 3.3 -> 2.3 ms, back-transform 2.5 -> 2.2 ms per decomposition
     const long long t128 = (long long)((d.M + 127) / 128) * ((d.N + 127) / 128) * d.batch;
     if (large && smallk > 0 && d.K <= smallk && t128 < 2LL * c->num_sms) large = false;
   }

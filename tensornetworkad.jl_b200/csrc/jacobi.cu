@@ -274,10 +274,6 @@ __global__ void k_fill_random(double* p, long long n, unsigned long long seed) {
   }
 }
 
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 
 }  // namespace
 
@@ -305,14 +301,14 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   const int npairs = p / 2;
   const int mchunks = (int)(mpad / RC), vchunks = (int)(ldv / RC);
 
-  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
-  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
+  static std::atomic<unsigned long long> attr_devs{0};   // kernel attributes are per device: one bit per device id (set after the attribute call: a racing thread at worst repeats it)
+  const bool attr_set = (attr_devs.load(std::memory_order_acquire) >> (c->device & 63)) & 1ULL;
   const size_t smem_gram = (size_t)JP * XLD * sizeof(double);
   const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gram));
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    attr_devs |= 1ULL << (c->device & 63);
+    attr_devs.fetch_or(1ULL << (c->device & 63), std::memory_order_release);
   }
 
   Tens G = t_alloc(c, {mpad, N}, true);
@@ -363,16 +359,16 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
   const double tol = std::max(8.0, 2.0 * std::sqrt((double)m)) * eps;
   // numerically-null threshold on squared column norms: (4 eps)^2 max(m,n) |A|_F^2
   double nullfac = 16.0 * eps * eps * (double)std::max(m, n);
-  if (const char* nr = getenv("TNAD_NULL_REL")) {   // experiment: freeze columns below nr * |A|_F
+  if (const char* nr = opt_s(c, "TNAD_NULL_REL")) {   // experiment: freeze columns below nr * |A|_F
     const double v = atof(nr);
     if (v > 0.0) nullfac = v * v;
   }
   double* fro2 = c->scal + 18;
   reduce(c, RED_SUMSQ, G, nullptr, fro2);
-  const bool debug = env_int("TNAD_JACOBI_DEBUG", 0) != 0;
-  const bool cross_mode = env_int("TNAD_JACOBI_CROSS", 0) != 0;
-  const int max_inner = env_int("TNAD_JACOBI_INNER", 1);
-  const int max_sweeps = env_int("TNAD_JACOBI_SWEEPS", 60);
+  const bool debug = opt_i(c, "TNAD_JACOBI_DEBUG", 0) != 0;
+  const bool cross_mode = opt_i(c, "TNAD_JACOBI_CROSS", 0) != 0;
+  const int max_inner = opt_i(c, "TNAD_JACOBI_INNER", 1);
+  const int max_sweeps = opt_i(c, "TNAD_JACOBI_SWEEPS", 60);
 
   SvdResult res;
   double prev_off = 1e300;
@@ -501,12 +497,12 @@ static SvdResult svd_jacobi_impl(tnad_ctx* c, const Tens& Ain0, bool sym, int de
 // X[:, (I,J)] <- X[:, (I,J)] * W_pair for every pair of the round (X has ld rows in nchunks 128-row chunks)
 void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int p, int round, const double* Wbuf,
                            const int* skip, cudaStream_t st) {
-  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
-  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
+  static std::atomic<unsigned long long> attr_devs{0};   // kernel attributes are per device: one bit per device id (set after the attribute call: a racing thread at worst repeats it)
+  const bool attr_set = (attr_devs.load(std::memory_order_acquire) >> (c->device & 63)) & 1ULL;
   const size_t smem_upd = (size_t)(JP * XLD + JP * WLD) * sizeof(double);
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_jacobi_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    attr_devs |= 1ULL << (c->device & 63);
+    attr_devs.fetch_or(1ULL << (c->device & 63), std::memory_order_release);
   }
   k_jacobi_update<<<dim3(p / 2, nchunks), 256, smem_upd, st ? st : c->stream>>>(X, ld, nchunks, nullptr, 0, p, round, Wbuf, skip,
       c->ktiming ? reinterpret_cast<unsigned long long*>(c->scal + 21) : nullptr);
@@ -514,7 +510,10 @@ void jacobi_rotate_columns(tnad_ctx* c, double* X, int64_t ld, int nchunks, int 
 }
 
 SvdResult svd_jacobi(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* V0, bool complete_null) {
-  return svd_jacobi_impl(c, A, sym_add_transpose, 0, V0, complete_null);
+  SvdResult r = svd_jacobi_impl(c, A, sym_add_transpose, 0, V0, complete_null);
+  const int64_t m = r.U.dim[0], n = r.V.dim[0], k = r.S.dim[0];
+  signfix_cols(c, r.U.p, m, m, r.V.p, n, n, k);   // canonical gauge
+  return r;
 }
 
 }  // namespace tnad

@@ -561,8 +561,8 @@ __global__ void __launch_bounds__(256) k_dc_rot_s(int m2, const int* __restrict_
   }
 }
 
-void leaf_plan(int64_t n, int& s, int& L) {
-  const char* ev = getenv("TNAD_DC_LEAF");
+void leaf_plan(const tnad_ctx* c, int64_t n, int& s, int& L) {
+  const char* ev = opt_s(c, "TNAD_DC_LEAF");
   const int smax = ev ? std::max(4, std::min(64, atoi(ev))) : 16;   // measured at n = 2048: 16 -> 2.2 ms, 32 -> 2.5, 64 -> 4.9
   L = 0;
   while ((n + (1LL << L) - 1) / (1LL << L) > smax) ++L;
@@ -575,7 +575,7 @@ void leaf_plan(int64_t n, int& s, int& L) {
 void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam, Tens& Z, int64_t& Nout) {
   TNAD_REQUIRE(n >= 1, "stedc: empty problem");
   int s, L;
-  leaf_plan(n, s, L);
+  leaf_plan(c, n, s, L);
   const int64_t N = (int64_t)s << L;
   Nout = N;
   cudaStream_t st = c->stream;
@@ -615,7 +615,7 @@ void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam
     double* lam_out = lamB.p;
     Tens* Qin = &Qa;
     Tens* Qout = &Qb;
-    const bool debug = getenv("TNAD_DC_DEBUG") && atoi(getenv("TNAD_DC_DEBUG")) > 1;
+    const bool debug = opt_i(c, "TNAD_DC_DEBUG", 0) > 1;
     for (int lvl = 0; lvl < L; ++lvl) {
       const int m = s << lvl, m2 = 2 * m;
       cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, e4 = nullptr;

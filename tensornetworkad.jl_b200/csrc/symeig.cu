@@ -451,10 +451,6 @@ __global__ void k_ns_factor(double* T, long long n) {
   }
 }
 
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 
 }  // namespace
 
@@ -499,23 +495,23 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
   const int chunks = (int)((N + 127) / 128);
   const int64_t ld = (int64_t)chunks * 128;   // rows padded to the 128-row chunks of the panel kernel
   const size_t smem_upd = (size_t)(2 * JP * BLD) * sizeof(double);
-  static unsigned long long attr_devs = 0;   // kernel attributes are per device: one bit per device id
-  const bool attr_set = (attr_devs >> (c->device & 63)) & 1ULL;
+  static std::atomic<unsigned long long> attr_devs{0};   // kernel attributes are per device: one bit per device id (set after the attribute call: a racing thread at worst repeats it)
+  const bool attr_set = (attr_devs.load(std::memory_order_acquire) >> (c->device & 63)) & 1ULL;
   if (!attr_set) {
     TNAD_CUDA(cudaFuncSetAttribute(k_sym_update_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    attr_devs |= 1ULL << (c->device & 63);
+    attr_devs.fetch_or(1ULL << (c->device & 63), std::memory_order_release);
   }
   const double eps = 2.220446049250313e-16;
   const double tolfac = 16.0 * eps;   // |m_pq| <= 16 eps |M|_F  (LAPACK-class absolute accuracy)
-  const bool debug = env_int("TNAD_JACOBI_DEBUG", 0) != 0;
-  const int max_inner = env_int("TNAD_SYMEIG_INNER", 1);
-  const int max_sweeps = env_int("TNAD_JACOBI_SWEEPS", 60);
-  const bool lookahead = env_int("TNAD_LOOKAHEAD", 1) != 0 && npairs >= 4;
-  const bool use_graph = env_int("TNAD_GRAPH", 1) != 0 && !c->ktiming;
-  const bool cross_mode = env_int("TNAD_SYMEIG_CROSS", 1) != 0;
+  const bool debug = opt_i(c, "TNAD_JACOBI_DEBUG", 0) != 0;
+  const int max_inner = opt_i(c, "TNAD_SYMEIG_INNER", 1);
+  const int max_sweeps = opt_i(c, "TNAD_JACOBI_SWEEPS", 60);
+  const bool lookahead = opt_i(c, "TNAD_LOOKAHEAD", 1) != 0 && npairs >= 4;
+  const bool use_graph = opt_i(c, "TNAD_GRAPH", 1) != 0 && !c->ktiming;
+  const bool cross_mode = opt_i(c, "TNAD_SYMEIG_CROSS", 1) != 0;
   double* fro2 = c->scal + 18;
   unsigned long long* offbits = reinterpret_cast<unsigned long long*>(c->scal + 16);
-  cudaStream_t S1 = c->stream, S2 = c->stream2, S3 = env_int("TNAD_S3", 0) ? c->stream3 : c->stream2;
+  cudaStream_t S1 = c->stream, S2 = c->stream2, S3 = opt_i(c, "TNAD_S3", 0) ? c->stream3 : c->stream2;
 
   // ---- cached workspace ------------------------------------------------------------------------------------
   if (!c->symcache || c->symcache->n != n || c->symcache->max_inner != max_inner + (cross_mode ? 100 : 0)) {
@@ -536,7 +532,7 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
     // measured at n = 2048 (528 blocks): 64 -> 750 ms, 296 -> 760, 420 -> 681, 480 -> 738, 528 -> 857 per 11 SVDs
     const int nblocks = npairs * (npairs + 1) / 2;
     const int fill_default = nblocks <= 4 * c->num_sms ? (4 * nblocks) / 5 : 2 * c->num_sms;
-    const int prio_fill = std::min(env_int("TNAD_PRIO_FILL", fill_default), nblocks);
+    const int prio_fill = std::min(opt_i(c, "TNAD_PRIO_FILL", fill_default), nblocks);
     const size_t plist_stride = (size_t)2 * std::max(2 * npairs, prio_fill);
     sc->plist_stride = plist_stride;
     std::vector<int> plist_h((size_t)nr * plist_stride + 8, 0);
@@ -772,6 +768,7 @@ SvdResult svd_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, cons
   k_sym_finalize<<<(int)n, 128, 0, c->stream>>>(Q.p, ld, dperm, dsgn, n, U.p, V.p);
   LAUNCH_CHECK(c);
   TNAD_CUDA(cudaMemcpyAsync(S.p, dsval, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  signfix_cols(c, U.p, n, n, V.p, n, n, n);
   sync(c);
   res.U = U;
   res.V = V;

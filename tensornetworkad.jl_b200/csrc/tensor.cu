@@ -184,4 +184,17 @@ void timing_end(tnad_ctx* c) {
   c->spans.clear();
 }
 
+const char* opt_s(const tnad_ctx* c, const char* name) {
+  auto it = c->opts.find(name);
+  return it == c->opts.end() ? nullptr : it->second.c_str();
+}
+int opt_i(const tnad_ctx* c, const char* name, int dflt) {
+  const char* v = opt_s(c, name);
+  return v ? atoi(v) : dflt;
+}
+double opt_d(const tnad_ctx* c, const char* name, double dflt) {
+  const char* v = opt_s(c, name);
+  return v ? atof(v) : dflt;
+}
+
 }  // namespace tnad

@@ -1047,12 +1047,15 @@ __global__ void k_larft(const double* __restrict__ G, int ldg, const double* __r
 
 __global__ void k_gather_cols(const double* __restrict__ Q, long long ldq, const int* __restrict__ perm,
                               const double* __restrict__ sgn, long long n, double* __restrict__ U, double* __restrict__ V) {
+  // fused: sort by |lambda| (perm), V = U sign(lambda), canonical column sign (largest-magnitude entry positive)
+  __shared__ double sh[SIGNFIX_SH];
   const long long j = blockIdx.x;
   const double* src = Q + (long long)perm[j] * ldq;
-  const double s = sgn[j];
+  const double g = block_canonical_sign(src, n, sh);
+  const double s = sgn[j] * g;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     const double v = src[i];
-    U[i + j * n] = v;
+    U[i + j * n] = v * g;
     V[i + j * n] = v * s;
   }
 }
@@ -1073,16 +1076,12 @@ __global__ void k_load_jw(double* H, long long ldh, const double* __restrict__ A
 // U[:, q] = sqrt(2) Z[0:m, pos[q]], V[:, q] = sqrt(2) Z[m:m+n, pos[q]]
 __global__ void k_gather_jw(const double* __restrict__ Z, long long ldz, const int* __restrict__ pos, long long m, long long n,
                             double* __restrict__ U, double* __restrict__ V) {
+  __shared__ double sh[SIGNFIX_SH];
   const long long q = blockIdx.x;
   const double* src = Z + (long long)pos[q] * ldz;
-  const double r2 = 1.4142135623730951;
+  const double r2 = 1.4142135623730951 * block_canonical_sign(src, m, sh);   // canonical gauge: largest |U[:, q]| entry positive
   for (long long i = threadIdx.x; i < m; i += blockDim.x) U[i + q * m] = r2 * src[i];
   for (long long i = threadIdx.x; i < n; i += blockDim.x) V[i + q * n] = r2 * src[m + i];
-}
-
-int env_i(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
 }
 
 Tens view2(double* p, int64_t rows, int64_t cols, int64_t ld) {
@@ -1102,7 +1101,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
   cudaStream_t st = c->stream;
   // columns [0, j_tail) go through the grid-wide panel kernel, the rest (trailing order t <= 416) through the cluster kernel
   int64_t j_tail = n;
-  if (env_i("TNAD_SYTRD_TAIL", 1) && n >= 3) {
+  if (opt_i(c, "TNAD_SYTRD_TAIL", 1) && n >= 3) {
     j_tail = n > TC_TMAX ? ((n - TC_TMAX + nb - 1) / nb) * nb : 0;
     if (n - j_tail < 3) j_tail = n;
   }
@@ -1117,17 +1116,17 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     TNAD_REQUIRE(per_sm >= 1, "sytrd: panel kernel does not fit on an SM");
     const int G = c->num_sms;
     const int64_t ldp = n;
-    const bool one_barrier = env_i("TNAD_SYTRD_1B", 1) != 0;
+    const bool one_barrier = opt_i(c, "TNAD_SYTRD_1B", 1) != 0;
     const int64_t NQ = (n + 3) / 4, NL = 4 * ((NQ + G - 1) / G);
     const size_t smem1 = (size_t)(8 * NL + 2 * NL * S1_NB + 80 + 8 * S1_NB + 24) * sizeof(double);
     Tens upart, spart1, pub, redo, prof;
     size_t smem_total = 0;
     int cache_cap_max = 0;
     double theta = 0.1;
-    if (const char* ev = getenv("TNAD_SYTRD_THETA")) theta = atof(ev);
+    theta = opt_d(c, "TNAD_SYTRD_THETA", theta);
     if (one_barrier) {
       TNAD_REQUIRE(smem1 <= 200 * 1024, "sytrd: matrix too large");
-      smem_total = env_i("TNAD_SYTRD_CACHE", 1) ? (size_t)(232448 - 256) : smem1;   // everything left of the 227 KB goes to the column cache
+      smem_total = opt_i(c, "TNAD_SYTRD_CACHE", 1) ? (size_t)(232448 - 256) : smem1;   // everything left of the 227 KB goes to the column cache
       cache_cap_max = (int)((smem_total - smem1) / sizeof(double)) & ~1;
       TNAD_CUDA(cudaFuncSetAttribute(k_sytrd_panel1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
       upart = t_alloc(c, {4 * NQ, (int64_t)G, 2});
@@ -1143,8 +1142,8 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     unsigned int* bar = reinterpret_cast<unsigned int*>(ctl.p);
     int* err = reinterpret_cast<int*>(ctl.p + 16 * (int64_t)G + 16);
     unsigned int bar_base = 0;
-    int dbg = env_i("TNAD_SYTRD_DBG", 0);
-    int bar_mode = env_i("TNAD_SYTRD_BAR", 1);   // 1: single release-add counter (measured 3.6k vs 4.4k cycles per barrier), 0: per-CTA flags
+    int dbg = opt_i(c, "TNAD_SYTRD_DBG", 0);
+    int bar_mode = opt_i(c, "TNAD_SYTRD_BAR", 1);   // 1: single release-add counter (measured 3.6k vs 4.4k cycles per barrier), 0: per-CTA flags
     unsigned int ctr_base = 0;
     for (int64_t j0 = 0; j0 < nref; j0 += nb) {
       int nbc = (int)std::min<int64_t>(nb, nref - j0);
@@ -1161,7 +1160,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
       const size_t smem_launch = use_cache ? smem_total : smem1;
       double *upp = upart.p, *spp = spart1.p, *pubp = pub.p;
       int* redop = reinterpret_cast<int*>(redo.p);
-      long long* profp = env_i("TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(prof.p) : nullptr;
+      long long* profp = opt_i(c, "TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(prof.p) : nullptr;
       void* args1[] = {&Ac, &lda_, &ni, &j0i, &nbc, &P1p, &P2p, &ldp_, &Vh, &ldv_, &tau, &dd, &ee, &upp, &spp, &pubp, &bar, &bar_base, &err, &theta, &redop, &profp, &bar_mode, &ctr_base, &cache_cap};
       {
         KTimer kt(c, KF_EIG);
@@ -1191,7 +1190,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     TNAD_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     sync(c);
     if (herr) fail(TNAD_ERR_INTERNAL, "sytrd: grid barrier timed out");
-    if (one_barrier && env_i("TNAD_DC_DEBUG", 0)) {
+    if (one_barrier && opt_i(c, "TNAD_DC_DEBUG", 0)) {
       int rc = 0;
       TNAD_CUDA(cudaMemcpy(&rc, redo.p, sizeof(int), cudaMemcpyDeviceToHost));
       fprintf(stderr, "[tnad dc] sytrd: %d of %lld columns redone (cancellation guard, theta %.3g)\n", rc, (long long)nref, theta);
@@ -1231,7 +1230,7 @@ void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t l
     long long lda_ = lda, ldv_ = ldv;
     int ni = (int)n, jt = (int)j_tail;
     Tens tp = t_alloc(c, {8}, true);
-    long long* tprof = env_i("TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(tp.p) : nullptr;
+    long long* tprof = opt_i(c, "TNAD_DC_DEBUG", 0) ? reinterpret_cast<long long*>(tp.p) : nullptr;
     {
       KTimer kt(c, KF_EIG);
       TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_sytrd_tail_cluster, Ac, lda_, ni, jt, Vh, ldv_, tau, dd, ee, tprof));
@@ -1261,7 +1260,7 @@ int64_t sytrd_vcols(int64_t n) { return (n + 127) / 128 * 128; }
 void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int64_t n, double* Z, int64_t ldz, int64_t ncols) {
   const int64_t nref = n >= 3 ? n - 2 : 0;
   if (nref == 0) return;
-  const int kb = env_i("TNAD_APPLYQ_NB", 128) >= 128 ? 128 : 64;   // measured: 128 wins at n = 2048 (2.5 vs 3.4 ms) and 6400 (46 vs 66 ms)
+  const int kb = opt_i(c, "TNAD_APPLYQ_NB", 128) >= 128 ? 128 : 64;   // measured: 128 wins at n = 2048 (2.5 vs 3.4 ms) and 6400 (46 vs 66 ms)
   const int64_t npan = (nref + kb - 1) / kb;
   TNAD_REQUIRE(npan * kb <= sytrd_vcols(n), "apply_q: reflector store too narrow");
   TNAD_CUDA(cudaFuncSetAttribute(k_larft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kb * kb + kb) * sizeof(double))));
@@ -1303,7 +1302,7 @@ static void eigh_dc(tnad_ctx* c, Tens& Aw, int64_t n, std::vector<double>& lh, T
     else amax = 1.0;
   }
   Tens Vh = t_alloc(c, {n, sytrd_vcols(n)}, true), tau = t_alloc(c, {sytrd_vcols(n)}, true), dd = t_alloc(c, {n}), ee = t_alloc(c, {n}, true);
-  const bool debug = env_i("TNAD_DC_DEBUG", 0) != 0;
+  const bool debug = opt_i(c, "TNAD_DC_DEBUG", 0) != 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (debug)
     for (auto& e : ev) e = get_event(c);
@@ -1444,13 +1443,12 @@ SvdResult svd_general_dc(tnad_ctx* c, const Tens& A4) {
 }
 
 SvdResult svd_symmetric_auto(tnad_ctx* c, const Tens& A, bool sym_add_transpose, const Tens* Q0) {
-  const int mode = env_i("TNAD_SYMEIG", -1);
+  const int mode = opt_i(c, "TNAD_SYMEIG", -1);
   const int64_t n = A.dim[0];
   // the direct solver needs cooperative (co-resident) launches; a device / partition without them keeps the Jacobi path
-  int coop = 0;
-  TNAD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+  const int coop = c->coop_launch;
   TNAD_REQUIRE(coop || mode != 2, "TNAD_SYMEIG=2 needs cooperative kernel launches, which this device does not support");
-  const bool dc = coop && (mode == 2 || (mode < 0 && n >= env_i("TNAD_DC_MIN", 48)));
+  const bool dc = coop && (mode == 2 || (mode < 0 && n >= opt_i(c, "TNAD_DC_MIN", 48)));
   return dc ? svd_symmetric_dc(c, A, sym_add_transpose) : svd_symmetric(c, A, sym_add_transpose, Q0);
 }
 

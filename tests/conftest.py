@@ -29,3 +29,24 @@ def golden():
         pub = json.load(f)
     vec = np.load(os.path.join(ROOT, "tests", "golden", "vectors.npz"))
     return pub, vec
+
+
+@pytest.fixture
+def opt(ctx):
+    """Set A/B options of the shared context for one test (tnad_set_option; the library reads the environment only
+    once, at tnad_create) and remove them afterwards."""
+    changed = []
+
+    def setter(name, value):
+        ctx.set_option(name, value)
+        changed.append(name)
+    yield setter
+    for name in changed:
+        ctx.set_option(name, None)
+
+
+@pytest.fixture(scope="session")
+def large():
+    """Oracle outputs at the benchmarked sizes (tests/golden/make_golden_large.py)."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "large.npz"))

@@ -251,11 +251,12 @@ def test_ctmrgstep_vs_oracle(ctx, D, chi):
     bulk = rng.standard_normal((D, D, D, D))
     bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
     c, e = O.init_random(bulk, chi, rng)
-    cr, er, vr = O.ctmrgstep(bulk, c, e)
+    cr, er, vr = O.ctmrgstep(bulk, c, e, signfix=True)
     cg, eg, vg = ctx.ctmrgstep(bulk, c, e)
     assert np.abs(vg - vr).max() < 1e-12
-    # corner / edge are defined up to column signs of U: compare gauge invariants
-    assert np.abs(np.abs(cg) - np.abs(cr)).max() < 1e-10 and np.abs(np.abs(eg) - np.abs(er)).max() < 1e-10
+    # corner / edge are defined up to column signs of U: both sides use the canonical gauge
+    # (largest-magnitude entry of every U column positive), so the tensors themselves are compared
+    assert np.abs(cg - cr).max() < 1e-10 and np.abs(eg - er).max() < 1e-10
     assert np.linalg.norm(cg) == pytest.approx(1.0, rel=1e-13) and np.linalg.norm(eg) == pytest.approx(1.0, rel=1e-13)
     assert np.allclose(cg, cg.T, atol=1e-15) and np.allclose(eg, np.transpose(eg, (2, 1, 0)), atol=1e-15)
 
@@ -295,11 +296,57 @@ def test_onsager_magnetisation(ctx, beta, chi, atol):
     assert abs(m - T.magofbeta(T.Ising(), beta)) < atol
 
 
-def test_magnetisation_gradient_sign_and_fd(ctx):
-    # test/ctmrg.jl:44-46: d magnetisation / d beta vs finite differences (loose, atol 1e-2)
-    f = lambda b: T.magnetisation(T.Ising(), b, 2, rng=np.random.default_rng(9), tol=1e-10, maxit=400, ctx=ctx)  # noqa: E731
-    fd = T.num_grad(f, 0.5, 1e-3)
-    assert 0.5 < fd < 5.0        # magnetisation rises steeply just above beta_c
+def test_magnetisation_gradient(ctx):
+    # test/ctmrg.jl:44-46: Zygote.gradient(beta -> magnetisation(Ising(), beta, 2), 0.5) against num_grad (atol 1e-2)
+    # and, tighter, against the oracle's reverse sweep on the same seeded :random environment
+    f = lambda b: T.magnetisation(T.Ising(), b, 2, rng=np.random.default_rng(9), ctx=ctx)  # noqa: E731
+    y, g = T.magnetisation_value_and_grad(T.Ising(), 0.5, 2, rng=np.random.default_rng(9), ctx=ctx)
+    assert y == pytest.approx(f(0.5), rel=1e-12)
+    assert abs(g - T.num_grad(f, 0.5, 1e-3)) < 1e-2
+    for beta, chi in [(0.5, 2), (0.6, 4), (0.3, 5)]:
+        a = O.model_tensor_ising(beta)
+        c0, e0 = O.init_random(a, chi, np.random.default_rng(9))
+        yo, go = O.magnetisation_value_and_dbeta(beta, chi, c0, e0, tol=1e-6, maxit=100)
+        y, g = T.magnetisation_value_and_grad(T.Ising(), beta, chi, rng=np.random.default_rng(9), ctx=ctx)
+        assert y == pytest.approx(yo, rel=1e-10, abs=1e-12) and g == pytest.approx(go, rel=1e-7, abs=1e-10)
+
+
+def test_magnetisation_readout_backward_vs_oracle(ctx):
+    rng = np.random.default_rng(4)
+    a, m = O.model_tensor_ising(0.45), O.mag_tensor_ising(0.45)
+    c, e = O.init_random(a, 6, rng)
+    got = ctx.magnetisation_backward(a, m, c, e, 0.7)
+    ref = O.magnetisation_readout_back(a, m, c, e, 0.7)
+    for g, r in zip(got, ref):
+        assert rel(g, r) < 1e-12
+
+
+def test_ctmrgstep_backward_vs_oracle(ctx):
+    # pullback of a single step in the canonical gauge
+    rng = np.random.default_rng(31)
+    D, chi = 3, 6
+    bulk = rng.standard_normal((D, D, D, D)); bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
+    c, e = O.init_random(bulk, chi, rng)
+    tape = []
+    O.ctmrgstep(bulk, c, e, tape=tape, signfix=True)
+    cb, eb = rng.standard_normal((chi, chi)), rng.standard_normal((chi, D, chi))
+    bo, co, eo = O.ctmrgstep_backward(bulk, tape[0], cb, eb)
+    bg, cg, eg = ctx.ctmrgstep_backward(bulk, c, e, cb, eb)
+    assert rel(bg, bo) < TOL_G and rel(cg, co) < TOL_G and rel(eg, eo) < TOL_G
+
+
+def test_expectationvalue_backward_vs_oracle(ctx):
+    rng = np.random.default_rng(6)
+    h = T.hamiltonian(T.Heisenberg())
+    A = O.indexperm_symmetrize(rng.standard_normal((2, 2, 2, 2, 2)))
+    ap, a = O.double_layer(A)
+    c, e = O.init_random(a, 5, rng)
+    t = {}
+    O.expectationvalue(h, ap, c, e, t)
+    ref = O.expectationvalue_back(c, e, t, 1.3)
+    got = ctx.expectationvalue_backward(h, ap, c, e, 1.3)
+    for g, r in zip(got, ref):
+        assert rel(g, r) < 1e-11
 
 
 def test_ctmrg_backward_vs_oracle(ctx):
@@ -403,6 +450,103 @@ def test_optimiseipeps_heisenberg(ctx, golden):
     assert abs(res.minimum - pub["heisenberg_energy_d2"]["value"]) < 1e-3
 
 
+# ---- parity at the sizes bench.py measures (BASELINE configs 2, 4, 5 and the TRG chi=64 part of the metric) ----------
+def _c4_A():
+    return O.indexperm_symmetrize(np.random.default_rng(0).standard_normal((4, 4, 4, 4, 2)))
+
+
+def test_c4_headline_energy_and_gradient_vs_oracle_fixture(ctx, large):
+    """BASELINE configs[3], d=4 chi=128 (n = chi D = 2048: the eigensolver's large path, 128x128 GEMM tiles, split-K
+    projector products): energy + gradient after maxit=3 (4 ctmrgsteps) against the frozen oracle run."""
+    h = T.hamiltonian(T.Heisenberg())
+    d, chi, maxit = [int(x) for x in large["c4_cfg"]]
+    e, g = T.energy_and_gradient(h, _c4_A(), chi, 0.0, maxit, ctx=ctx)
+    assert ctx.last_steps == int(large["c4_steps"]) == maxit + 1
+    assert e == pytest.approx(float(large["c4_e"]), rel=TOL_E)
+    assert rel(g, large["c4_grad"]) < TOL_G
+
+
+def test_c4_headline_vs_oracle_live(ctx):
+    """The same configuration at maxit=1 against the oracle run on this machine's LAPACK (about 4 s of CPU)."""
+    h = T.hamiltonian(T.Heisenberg())
+    A = _c4_A()
+    eo, go = O.energy_value_and_grad(h, A, 128, 0.0, 1)
+    e, g = T.energy_and_gradient(h, A, 128, 0.0, 1, ctx=ctx)
+    assert e == pytest.approx(eo, rel=TOL_E) and rel(g, go) < TOL_G
+
+
+@pytest.mark.parametrize("beta", [0.3, 0.5])
+def test_c2_ising_chi64_raw(ctx, large, beta):
+    """BASELINE configs[1]: CTMRG Ising chi=64, tol=1e-10, :raw environment: step count and converged spectrum."""
+    a = T.model_tensor(T.Ising(), beta)
+    c0, e0 = ctx.ctmrg_init_raw(a, 64)
+    co, ed, vals, steps = ctx.ctmrg(a, c0, e0, 1e-10, 5000)
+    assert steps == int(large[f"c2_raw_{beta}_steps"])
+    assert np.abs(vals - large[f"c2_raw_{beta}_vals"]).max() < 1e-9
+    # the :raw environment keeps the Z2 symmetry: no spontaneous magnetisation on either side
+    assert ctx.magnetisation_readout(a, T.mag_tensor(T.Ising(), beta), co, ed) < 1e-6
+
+
+@pytest.mark.parametrize("beta", [0.3, 0.5])
+def test_c2_ising_chi64_random_env(ctx, large, beta):
+    """configs[1] with the :random environment of a host-seeded generator (ctmrg.jl:66-72): step count, spectrum and
+    magnetisation (Onsager above beta_c)."""
+    a, m = T.model_tensor(T.Ising(), beta), T.mag_tensor(T.Ising(), beta)
+    c0, e0 = O.init_random(a, 64, np.random.default_rng(3))
+    co, ed, vals, steps = ctx.ctmrg(a, c0, e0, 1e-10, 5000)
+    assert abs(steps - int(large[f"c2_random_{beta}_steps"])) <= 2      # tol sits on the rounding floor of ||dvals||
+    assert np.abs(vals - large[f"c2_random_{beta}_vals"]).max() < 1e-8
+    mag = ctx.magnetisation_readout(a, m, co, ed)
+    assert mag == pytest.approx(float(large[f"c2_random_{beta}_mag"]), abs=1e-8)
+    assert mag == pytest.approx(T.magofbeta(T.Ising(), beta), abs=1e-6)
+
+
+def test_trg_chi64_vs_oracle_fixture(ctx, large):
+    """TRG chi=64 (third part of BASELINE's metric): 7 iterations, the last two split full 4096 x 4096 matrices."""
+    beta, chi, niter = float(large["trg64_cfg"][0]), int(large["trg64_cfg"][1]), int(large["trg64_cfg"][2])
+    lnz, g = T.trg_value_and_grad(T.model_tensor(T.Ising(), beta), chi, niter, ctx=ctx)
+    assert lnz == pytest.approx(float(large["trg64_lnz"]), rel=TOL_E)
+    assert float(np.sum(g * T.dmodel_tensor(T.Ising(), beta))) == pytest.approx(float(large["trg64_dbeta"]), rel=TOL_G)
+
+
+def test_c5a_step_vs_oracle_fixture(ctx, large):
+    """BASELINE configs[4]: one ctmrgstep at d=5, chi=256 (n = 6400) from a seeded :random environment: spectrum and
+    probes of the sign-fixed corner / edge."""
+    A = O.indexperm_symmetrize(np.random.default_rng(0).standard_normal((5, 5, 5, 5, 2)))
+    _, a = O.double_layer(A)
+    c0, e0 = O.init_random(a, 256, np.random.default_rng(1))
+    co, ed, vals = ctx.ctmrgstep(a, c0, e0)
+    rng = np.random.default_rng(7)
+    w1, w2, w3 = rng.standard_normal(256), rng.standard_normal(25), rng.standard_normal(256)
+    assert np.abs(vals - large["c5a_vals"]).max() < 1e-10
+    assert np.abs(np.diag(co) - large["c5a_corner_diag"]).max() < 1e-9
+    assert np.abs(co @ w1 - large["c5a_corner_w"]).max() < 1e-8
+    assert np.abs(np.einsum("ijk,i,k->j", ed, w1, w3) - large["c5a_edge_w"]).max() < 1e-8
+    assert np.abs(np.einsum("ijk,j,k->i", ed, w2, w3) - large["c5a_edge_w2"]).max() < 1e-8
+
+
+def test_trg_sweep_matches_single_instances(ctx):
+    """tnad_trg_sweep (in-library fan-out, one context per device) against instance-by-instance calls."""
+    betas = [0.3, 0.4, 0.5]
+    ts = [T.model_tensor(T.Ising(), b) for b in betas]
+    lnz, grads = T.trg_sweep(ts, 8, 6, ngpu=1, grad=True)
+    for i, b in enumerate(betas):
+        l1, g1 = T.trg_value_and_grad(ts[i], 8, 6, ctx=ctx)
+        assert lnz[i] == pytest.approx(l1, rel=1e-13)
+        assert float(np.sum(grads[i] * T.dmodel_tensor(T.Ising(), b))) == pytest.approx(
+            float(np.sum(g1 * T.dmodel_tensor(T.Ising(), b))), rel=1e-10)
+
+
+def test_tape_outliving_close_is_safe():
+    """a tape must not outlive its context's stream: Context.close() frees outstanding tapes first, and
+    tnad_destroy refuses while tapes are alive."""
+    c2 = T.Context(0)
+    lnz, tape = c2.trg_forward(T.model_tensor(T.Ising(), 0.4), 4, 3, want_tape=True)
+    assert c2.lib.tnad_destroy(c2.h) == 1          # TNAD_ERR_ARG: a live tape
+    c2.close()                                     # frees the tape, then destroys
+    assert tape.h is None
+
+
 def test_headline_shape_runs_and_is_consistent(ctx):
     # d=4, chi=128 (BASELINE configs[3]) at maxit=1: size-independent checks -- the gradient of the
     # (scale-invariant) energy is orthogonal to A, energy reproducible call to call, launch counter moves.
@@ -427,16 +571,16 @@ def test_sharded_step_single_rank_vs_oracle(ctx, D, chi):
     bulk = rng.standard_normal((D, D, D, D))
     bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
     c, e = O.init_random(bulk, chi, rng)
-    cr, er, vr = O.ctmrgstep(bulk, c, e)
+    cr, er, vr = O.ctmrgstep(bulk, c, e, signfix=True)
     sh = ShardedCTMRG(ctx, chi, D)
     sh.load(bulk, c, e)
     sh.step()
     cg, eg, vg = sh.result()
     assert np.abs(vg - vr).max() < 1e-12
-    assert np.abs(np.abs(cg) - np.abs(cr)).max() < 1e-10 and np.abs(np.abs(eg) - np.abs(er)).max() < 1e-10
+    assert np.abs(cg - cr).max() < 1e-10 and np.abs(eg - er).max() < 1e-10
     # and against the unsharded C-ABI step on the same inputs
     c1, e1, v1 = ctx.ctmrgstep(bulk, c, e)
-    assert np.abs(vg - v1).max() < 1e-12 and np.abs(np.abs(cg) - np.abs(c1)).max() < 1e-11
+    assert np.abs(vg - v1).max() < 1e-12 and np.abs(cg - c1).max() < 1e-11
 
 
 @pytest.mark.gpu
@@ -525,10 +669,10 @@ def _sym_cases(n, rng):
 @pytest.mark.gpu
 @pytest.mark.parametrize("one_barrier", ["1", "0"])
 @pytest.mark.parametrize("n", [3, 4, 10, 33, 97, 130, 259, 600])
-def test_sytrd_backward_error(ctx, n, one_barrier, monkeypatch):
+def test_sytrd_backward_error(ctx, n, one_barrier, opt):
     """A = Q T Q' to machine precision for both panel kernels, including rank-deficient input (the cancellation
     guard of the one-barrier kernel) and sizes that are odd / not multiples of the ownership quad."""
-    monkeypatch.setenv("TNAD_SYTRD_1B", one_barrier)
+    opt("TNAD_SYTRD_1B", one_barrier)
     rng = np.random.default_rng(100 + n)
     for name, a in _sym_cases(n, rng):
         d, e, q = ctx.sytrd(a)
@@ -542,9 +686,9 @@ def test_sytrd_backward_error(ctx, n, one_barrier, monkeypatch):
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["1", "2"])
 @pytest.mark.parametrize("n", [64, 300, 520])
-def test_svd_sym_both_solvers(ctx, n, mode, monkeypatch):
+def test_svd_sym_both_solvers(ctx, n, mode, opt):
     """tnad_svd_sym through the block-Jacobi solver (1) and the tridiagonal divide-and-conquer solver (2)."""
-    monkeypatch.setenv("TNAD_SYMEIG", mode)
+    opt("TNAD_SYMEIG", mode)
     rng = np.random.default_rng(n)
     for name, a in _sym_cases(n, rng):
         u, s, v = ctx.svd_sym(a)
@@ -557,14 +701,14 @@ def test_svd_sym_both_solvers(ctx, n, mode, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_energy_gradient_same_with_both_solvers(ctx, monkeypatch):
+def test_energy_gradient_same_with_both_solvers(ctx, opt):
     """The headline path (energy + gradient) must not depend on which eigensolver ran (chi*D = 256 >= TNAD_DC_MIN)."""
     rng = np.random.default_rng(5)
     h = T.hamiltonian(T.Heisenberg())
     A = T.indexperm_symmetrize(T.SquareIPEPS(rng.standard_normal((2, 2, 2, 2, 2)))).bulk
     out = {}
     for mode in ("1", "2"):
-        monkeypatch.setenv("TNAD_SYMEIG", mode)
+        opt("TNAD_SYMEIG", mode)
         out[mode] = ctx.energy(h, A, 64, 0.0, 4, grad=True)
     e1, g1 = out["1"]
     e2, g2 = out["2"]
@@ -576,9 +720,9 @@ def test_energy_gradient_same_with_both_solvers(ctx, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["zero", "identity", "diag_repeated", "tiny_scale", "denormal_squares", "huge_scale", "rank_one", "block_diag"])
-def test_svd_sym_direct_solver_degenerate_inputs(ctx, kind, monkeypatch):
+def test_svd_sym_direct_solver_degenerate_inputs(ctx, kind, opt):
     """Inputs on which every reflector / merge degenerates (tau = 0, rho = 0, full deflation)."""
-    monkeypatch.setenv("TNAD_SYMEIG", "2")
+    opt("TNAD_SYMEIG", "2")
     rng = np.random.default_rng(9)
     n = 150
     if kind == "zero":
@@ -615,13 +759,13 @@ def test_svd_sym_direct_solver_degenerate_inputs(ctx, kind, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("beta", [0.3, 0.44, 0.6])
-def test_trg_same_with_both_svd_routes(ctx, beta, monkeypatch):
+def test_trg_same_with_both_svd_routes(ctx, beta, opt):
     """TRG value + gradient through the one-sided Jacobi SVD and through the Jordan-Wielandt / direct-eigensolver route
     (rank-deficient splits: the null triplets enter svd_back only through the projectors)."""
     a = T.model_tensor(T.Ising(), beta)
     out = {}
     for mode in ("jacobi", "dc"):
-        monkeypatch.setenv("TNAD_TRG_SVD", mode)
+        opt("TNAD_TRG_SVD", mode)
         out[mode] = T.trg_value_and_grad(a, 12, 9, ctx=ctx)
     (l1, g1), (l2, g2) = out["jacobi"], out["dc"]
     assert abs(l1 - l2) <= 1e-12 * abs(l1)

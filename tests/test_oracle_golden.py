@@ -183,3 +183,60 @@ def test_norm_pullback():
     got = O._norm_back(ybar, x2, np.linalg.norm(x2))
     f = lambda x: np.sum(ybar * x / np.linalg.norm(x))  # noqa: E731
     assert np.allclose(got, O.num_grad(f, x2), atol=1e-7)
+
+
+# ---- round 2 additions: canonical gauge, magnetisation pullback, large-size fixtures -------------------------------
+def test_canonical_gauge_keeps_the_decomposition():
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((9, 9))
+    U, S, V = O.svd(A + A.T)
+    U2, V2 = O.canonical_gauge(U, V)
+    assert np.abs((U2 * S) @ V2.T - (A + A.T)).max() < 1e-13
+    top = U2[np.argmax(np.abs(U2), axis=0), np.arange(9)]
+    assert np.all(top > 0)
+    # the step is covariant under the gauge: invariants agree, corner differs at most by signs
+    bulk = rng.standard_normal((2, 2, 2, 2)); bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
+    c, e = O.init_random(bulk, 4, rng)
+    c1, e1, v1 = O.ctmrgstep(bulk, c, e)
+    c2, e2, v2 = O.ctmrgstep(bulk, c, e, signfix=True)
+    assert np.abs(v1 - v2).max() < 1e-14 and np.abs(np.abs(c1) - np.abs(c2)).max() < 1e-13
+
+
+def test_magnetisation_pullback_against_finite_differences():
+    # test/ctmrg.jl:44-46 differentiates magnetisation; here every piece of the oracle's reverse sweep is checked
+    rng = np.random.default_rng(9)
+    a, m = O.model_tensor_ising(0.5), O.mag_tensor_ising(0.5)
+    c, e = O.init_random(a, 4, rng)
+    ab, mb, cb, eb = O.magnetisation_readout_back(a, m, c, e)
+    dc, de = rng.standard_normal(c.shape), rng.standard_normal(e.shape)
+    da, dm = rng.standard_normal(a.shape), rng.standard_normal(a.shape)
+    eps = 1e-6
+    fd = (O.magnetisation_readout(a + eps * da, m + eps * dm, c + eps * dc, e + eps * de)
+          - O.magnetisation_readout(a - eps * da, m - eps * dm, c - eps * dc, e - eps * de)) / (2 * eps)
+    assert fd == pytest.approx(np.sum(ab * da) + np.sum(mb * dm) + np.sum(cb * dc) + np.sum(eb * de), rel=1e-7)
+    h = 1e-6
+    assert np.abs((O.mag_tensor_ising(0.5 + h) - O.mag_tensor_ising(0.5 - h)) / (2 * h) - O.dmag_tensor_ising(0.5)).max() < 1e-8
+    c0, e0 = O.init_random(a, 2, np.random.default_rng(9))
+    y, g = O.magnetisation_value_and_dbeta(0.5, 2, c0, e0, tol=1e-10, maxit=400)
+
+    def f(b):
+        ab_, mb_ = O.model_tensor_ising(b), O.mag_tensor_ising(b)
+        cc, ee, _, _ = O.ctmrg(ab_, c0, e0, 1e-10, 400)
+        return O.magnetisation_readout(ab_, mb_, cc, ee)
+    assert abs(g - (f(0.5 + 5e-4) - f(0.5 - 5e-4)) / 1e-3) < 1e-2       # the reference's own tolerance
+
+
+def test_large_fixture_is_consistent_with_known_answers():
+    import os
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "large.npz"))
+    # CTMRG chi=64 with a :random environment reproduces Onsager's magnetisation above beta_c (test/ctmrg.jl:37-42)
+    assert float(vec["c2_random_0.5_mag"]) == pytest.approx(O.magofbeta(0.5), abs=1e-10)
+    assert float(vec["c2_random_0.3_mag"]) < 1e-10
+    # LAPACK's two SVD drivers agree on step count and spectrum at chi=64 (the fixture's noise floor)
+    for beta in (0.3, 0.5):
+        assert int(vec[f"c2_raw_{beta}_steps"]) == int(vec[f"c2_raw_{beta}_steps_gesvd"])
+        assert float(vec[f"c2_raw_{beta}_vals_spread"]) < 1e-13
+    # TRG chi=64, 7 iterations at beta = 0.44 sits between the chi=20 published values' neighbours (sanity) and
+    # d lnZ / d beta is positive
+    assert 0.9 < float(vec["trg64_lnz"]) < 1.0 and float(vec["trg64_dbeta"]) > 1.0
+    assert int(vec["c4_steps"]) == 4 and vec["c4_grad"].shape == (4, 4, 4, 4, 2)
