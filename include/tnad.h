@@ -186,6 +186,10 @@ TNAD_API int tnad_svd_symmetrized(tnad_ctx* ctx, const double* A, int n, double*
 /* stages of the direct symmetric eigensolver (tridiag.cu / stedc.cu), exported for the parity tests:
    A = Q T Q' with T = tridiag(d, e) (Householder, LAPACK dsytrd semantics; Q explicit n x n) ... */
 TNAD_API int tnad_sytrd(tnad_ctx* ctx, const double* A, int n, double* d, double* e, double* Q);
+/* the same factorisation through the two-stage route (band.cu): dense -> band (half bandwidth 32, panel QR inside a
+   thread-block cluster + DMMA trailing updates) -> tridiagonal (systolic bulge chasing); Q = Q1 Q2 explicit.
+   band (33 x n, lower band storage of the intermediate band matrix) may be NULL.  n >= 3. */
+TNAD_API int tnad_sytrd2(tnad_ctx* ctx, const double* A, int n, double* d, double* e, double* Q, double* band);
 /* ... and all eigenpairs of tridiag(d, e), ascending (divide and conquer, LAPACK dstedc semantics) */
 TNAD_API int tnad_stedc(tnad_ctx* ctx, const double* d, const double* e, int n, double* lam, double* Z);
 /* permutedims(in, perm) (0-based perm, Julia semantics: out dim i = in dim perm[i]) */

@@ -73,6 +73,7 @@ SIGNATURES = {
                                  c_int_p, c_double_p, C.c_void_p, C.c_char_p, C.c_int]),
     "tnad_svd_symmetrized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
     "tnad_sytrd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tnad_sytrd2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tnad_stedc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_permute": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, c_int_p, C.c_void_p]),
     "tnad_ctmrg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -425,6 +426,14 @@ class Context:
         self.check(self.lib.tnad_sytrd(self.h, _p(a), n, _p(d), _p(e), _p(q)))
         return d, e[:n - 1], q
 
+    def sytrd2(self, a):
+        """A = Q tridiag(d, e) Q' through the two-stage route; also returns the intermediate band (33 x n)."""
+        a = farray(a)
+        n = a.shape[0]
+        d = np.empty(n); e = np.empty(max(n - 1, 1)); q = np.empty((n, n), order="F"); band = np.empty((33, n), order="F")
+        self.check(self.lib.tnad_sytrd2(self.h, _p(a), n, _p(d), _p(e), _p(q), _p(band)))
+        return d, e[:n - 1], q, band
+
     def stedc(self, d, e):
         d = np.ascontiguousarray(d, dtype=np.float64); e = np.ascontiguousarray(e, dtype=np.float64)
         n = d.size
@@ -477,6 +486,17 @@ class Context:
         self.check(self.lib.tnad_magnetisation_readout(self.h, _p(a), _p(m), D, _p(corner), _p(edge), chi,
                                                        C.byref(mag)))
         return mag.value
+
+    def magnetisation_backward(self, a, m, corner, edge, ybar=1.0):
+        """Pullback of the read-out: (da, dm, dcorner, dedge)."""
+        a, m = farray(a), farray(m)
+        D, chi = a.shape[0], np.shape(corner)[0]
+        corner, edge = farray(corner, (chi, chi)), farray(edge, (chi, D, chi))
+        da = np.empty(a.shape, order="F"); dm = np.empty(a.shape, order="F")
+        dc = np.empty((chi, chi), order="F"); de = np.empty((chi, D, chi), order="F")
+        self.check(self.lib.tnad_magnetisation_backward(self.h, _p(a), _p(m), D, _p(corner), _p(edge), chi, float(ybar),
+                                                        _p(da), _p(dm), _p(dc), _p(de)))
+        return da, dm, dc, de
 
 
 def trg_sweep(tensors, chi, niter, tol=1e-16, ngpu=1, devices=None, grad=False):

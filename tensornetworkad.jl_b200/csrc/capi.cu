@@ -275,6 +275,30 @@ int tnad_sytrd(tnad_ctx* c, const double* A, int n, double* d, double* e, double
   TNAD_API_END(c)
 }
 
+int tnad_sytrd2(tnad_ctx* c, const double* A, int n, double* d, double* e, double* Q, double* band) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(n >= 3 && d && e && Q, "tnad_sytrd2: bad arguments (n >= 3)");
+  Tens tA = t_in(c, A, {n, n});
+  Tens Aw = t_clone(c, tA);
+  const int64_t vc = sytrd_vcols(n), NP = chase_positions(n), ldv2 = 32 * NP;
+  Tens Yst = t_alloc(c, {n, vc}, true), tau1 = t_alloc(c, {vc}, true), dd = t_alloc(c, {n}), ee = t_alloc(c, {n}, true);
+  sy2sb(c, Aw.p, n, n, Yst.p, n, tau1.p);
+  Tens AB = t_alloc(c, {33, n});
+  extract_band(c, Aw.p, n, n, AB.p, 33);
+  Tens V2 = t_alloc(c, {ldv2, (int64_t)n - 2}, true), tau2 = t_alloc(c, {NP, (int64_t)n - 2}, true);
+  sb2st(c, AB.p, 33, n, dd.p, ee.p, V2.p, ldv2, tau2.p);
+  Tens Qm = t_alloc(c, {n, n}, true);
+  set_identity(c, Qm.p, n, n);
+  apply_q2(c, V2.p, ldv2, tau2.p, n, Qm.p, n, n);
+  apply_q(c, Yst.p, n, tau1.p, n, Qm.p, n, n, 32);
+  t_out(c, dd, d);
+  Tens ev = t_wrap(ee.p, {n - 1});
+  t_out(c, ev, e);
+  t_out(c, Qm, Q);
+  if (band) t_out(c, AB, band);
+  TNAD_API_END(c)
+}
+
 int tnad_stedc(tnad_ctx* c, const double* d, const double* e, int n, double* lam, double* Z) {
   TNAD_API_BEGIN(c)
   TNAD_REQUIRE(n >= 1 && d && lam && Z && (n == 1 || e), "tnad_stedc: bad arguments");

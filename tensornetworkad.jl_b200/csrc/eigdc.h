@@ -8,11 +8,19 @@ namespace tnad {
 void sytrd(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Vh, int64_t ldv, double* tau, double* dd, double* ee);
 int64_t sytrd_vcols(int64_t n);   // columns Vh / entries tau must provide (zero-initialised)
 // Z[0:n, 0:ncols] <- Q Z
-void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int64_t n, double* Z, int64_t ldz, int64_t ncols);
+// (offset: row distance between a reflector's column index and its unit element: 1 for sytrd, 32 for the band reduction)
+void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int64_t n, double* Z, int64_t ldz, int64_t ncols,
+             int64_t offset = 1);
 // All eigenpairs of the symmetric tridiagonal (dd, ee) of order n.  The problem is padded to N = s 2^L >= n
 // (s <= 64) with decoupled diagonal entries above the spectrum; lam (N) and Z (N x N, leading dimension N) come
 // back unsorted, the pad eigenvalues being the N - n largest, their eigenvectors unit vectors in the pad rows.
 void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam, Tens& Z, int64_t& N);
+// ---- two-stage route (band.cu) ----
+int64_t chase_positions(int64_t n);
+void extract_band(tnad_ctx* c, const double* A, int64_t lda, int64_t n, double* AB, int64_t ldab);
+void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t ldy, double* tau1);
+void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, double* ee, double* V2, int64_t ldv, double* tau2);
+void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, int64_t n, double* X, int64_t ldx, int64_t ncols);
 SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose);
 // general (rank-2 or rank-4 [(d1,d2),(d3,d4)] view) matrix through the Jordan-Wielandt embedding; only the r non-null
 // triplets are formed (rank_left = rank_right = r)

@@ -1257,8 +1257,10 @@ int64_t sytrd_vcols(int64_t n) { return (n + 127) / 128 * 128; }
 
 // Z[0:n, 0:ncols] <- Q Z with Q = H_0 ... H_{n-3} from sytrd (panels applied last to first, compact WY):
 // Gram matrices, T factors and V T of ALL panels come from three batched launches; each panel then costs two GEMMs.
-void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int64_t n, double* Z, int64_t ldz, int64_t ncols) {
-  const int64_t nref = n >= 3 ? n - 2 : 0;
+void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int64_t n, double* Z, int64_t ldz, int64_t ncols,
+             int64_t offset) {
+  // reflector of column j: unit element at row j + offset, so the last useful column is n - 2 - offset
+  const int64_t nref = n >= offset + 2 ? n - 1 - offset : 0;
   if (nref == 0) return;
   const int kb = opt_i(c, "TNAD_APPLYQ_NB", 128) >= 128 ? 128 : 64;   // measured: 128 wins at n = 2048 (2.5 vs 3.4 ms) and 6400 (46 vs 66 ms)
   const int64_t npan = (nref + kb - 1) / kb;
@@ -1278,7 +1280,7 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
   contract(c, "rpi,ijp->rjp", Vall, Tall, VT);
   Tens Y = t_alloc(c, {kb, ncols});
   for (int64_t pi = npan - 1; pi >= 0; --pi) {
-    const int64_t j0 = pi * kb, jr = j0 + 1, rows = n - jr;
+    const int64_t j0 = pi * kb, jr = j0 + offset, rows = n - jr;
     Tens Vp = view2(V + jr + j0 * ldv, rows, kb, ldv);
     Tens VTp = view2(VT.p + jr + pi * (int64_t)kb * n, rows, kb, n);
     Tens Zr = view2(Z + jr, rows, ncols, ldz);
@@ -1303,26 +1305,54 @@ static void eigh_dc(tnad_ctx* c, Tens& Aw, int64_t n, std::vector<double>& lh, T
   }
   Tens Vh = t_alloc(c, {n, sytrd_vcols(n)}, true), tau = t_alloc(c, {sytrd_vcols(n)}, true), dd = t_alloc(c, {n}), ee = t_alloc(c, {n}, true);
   const bool debug = opt_i(c, "TNAD_DC_DEBUG", 0) != 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // two-stage route (band.cu) from n >= TNAD_2STAGE_MIN on; TNAD_EIG_2STAGE = 0 | 1 forces one route
+  const int ts_mode = opt_i(c, "TNAD_EIG_2STAGE", -1);
+  const bool two_stage = n >= 67 && (ts_mode == 1 || (ts_mode < 0 && n >= opt_i(c, "TNAD_2STAGE_MIN", 768)));
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (debug)
     for (auto& e : ev) e = get_event(c);
   if (debug) TNAD_CUDA(cudaEventRecord(ev[0], st));
-  sytrd(c, Aw.p, n, n, Vh.p, n, tau.p, dd.p, ee.p);
-  if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
   Tens lam;
-  stedc(c, dd.p, ee.p, n, lam, Z, N);   // Z: N x N (ld N), lam: N, pads carry eigenvalues above the spectrum
-  if (debug) TNAD_CUDA(cudaEventRecord(ev[2], st));
-  apply_q(c, Vh.p, n, tau.p, n, Z.p, N, N);
-  if (debug) {
-    TNAD_CUDA(cudaEventRecord(ev[3], st));
-    TNAD_CUDA(cudaEventSynchronize(ev[3]));
-    float a = 0, b = 0, d3 = 0;
-    cudaEventElapsedTime(&a, ev[0], ev[1]);
-    cudaEventElapsedTime(&b, ev[1], ev[2]);
-    cudaEventElapsedTime(&d3, ev[2], ev[3]);
-    fprintf(stderr, "[tnad dc] n=%lld N=%lld sytrd %.2f ms  stedc %.2f ms  apply_q %.2f ms\n", (long long)n, (long long)N, a, b, d3);
-    for (auto& e : ev) c->event_pool.push_back(e);
+  if (two_stage) {
+    const int64_t NP = chase_positions(n), ldv2 = 32 * NP;
+    sy2sb(c, Aw.p, n, n, Vh.p, n, tau.p);                      // A = Q1 B Q1'
+    Tens AB = t_alloc(c, {33, n});
+    extract_band(c, Aw.p, n, n, AB.p, 33);
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
+    Tens V2 = t_alloc(c, {ldv2, n - 2}, true), tau2 = t_alloc(c, {NP, n - 2}, true);
+    sb2st(c, AB.p, 33, n, dd.p, ee.p, V2.p, ldv2, tau2.p);     // B = Q2 T Q2'
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[2], st));
+    stedc(c, dd.p, ee.p, n, lam, Z, N);
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[3], st));
+    apply_q2(c, V2.p, ldv2, tau2.p, n, Z.p, N, N);
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[4], st));
+    apply_q(c, Vh.p, n, tau.p, n, Z.p, N, N, 32);
+    if (debug) {
+      TNAD_CUDA(cudaEventRecord(ev[5], st));
+      TNAD_CUDA(cudaEventSynchronize(ev[5]));
+      float t[5];
+      for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+      fprintf(stderr, "[tnad dc] n=%lld N=%lld two-stage: sy2sb %.2f ms  chase %.2f ms  stedc %.2f ms  apply_q2 %.2f ms  apply_q1 %.2f ms\n",
+              (long long)n, (long long)N, t[0], t[1], t[2], t[3], t[4]);
+    }
+  } else {
+    sytrd(c, Aw.p, n, n, Vh.p, n, tau.p, dd.p, ee.p);
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
+    stedc(c, dd.p, ee.p, n, lam, Z, N);   // Z: N x N (ld N), lam: N, pads carry eigenvalues above the spectrum
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[2], st));
+    apply_q(c, Vh.p, n, tau.p, n, Z.p, N, N);
+    if (debug) {
+      TNAD_CUDA(cudaEventRecord(ev[3], st));
+      TNAD_CUDA(cudaEventSynchronize(ev[3]));
+      float a = 0, b = 0, d3 = 0;
+      cudaEventElapsedTime(&a, ev[0], ev[1]);
+      cudaEventElapsedTime(&b, ev[1], ev[2]);
+      cudaEventElapsedTime(&d3, ev[2], ev[3]);
+      fprintf(stderr, "[tnad dc] n=%lld N=%lld sytrd %.2f ms  stedc %.2f ms  apply_q %.2f ms\n", (long long)n, (long long)N, a, b, d3);
+    }
   }
+  if (debug)
+    for (auto& e : ev) c->event_pool.push_back(e);
   lh.resize((size_t)N);
   d2h(c, lh.data(), lam.p, (size_t)N);
   for (auto& v : lh) v *= amax;

@@ -781,3 +781,59 @@ def test_trg_same_with_both_svd_routes(ctx, beta, opt):
     da = O.dmodel_tensor_ising(beta)
     assert abs(l2 - lo) <= 1e-10 * abs(lo)
     assert abs(np.sum(g2 * da) - np.sum(go * da)) <= 1e-8 * abs(np.sum(go * da))
+
+
+# ---- two-stage tridiagonalisation (band.cu): dense -> band (cluster panel QR + DMMA updates) -> tridiagonal (systolic chase)
+def _band_dense(band, n, b=32):
+    B = np.zeros((n, n))
+    for j in range(n):
+        for o in range(min(b, n - 1 - j) + 1):
+            B[j + o, j] = band[o, j]
+            B[j, j + o] = band[o, j]
+    return B
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [3, 5, 33, 34, 35, 40, 65, 66, 97, 130, 259, 600, 1100])
+def test_sytrd2_backward_error(ctx, n):
+    """A = Q T Q' to machine precision through the two-stage route, incl. rank-deficient and graded input, sizes around
+    the panel / window boundaries (33, 34, 65, 66) and several chase CTAs (n = 1100: 35 positions)."""
+    rng = np.random.default_rng(200 + n)
+    for name, a in _sym_cases(n, rng):
+        d, e, q, band = ctx.sytrd2(a)
+        Tm = _tridiag(d, e)
+        nrm = np.linalg.norm(a, 2)
+        assert np.abs(q.T @ q - np.eye(n)).max() <= 3e-14, (name, n)
+        assert np.abs(q @ Tm @ q.T - a).max() <= 3e-14 * nrm, (name, n)
+        ev = np.linalg.eigvalsh(a)
+        assert np.abs(np.linalg.eigvalsh(Tm) - ev).max() <= 3e-14 * nrm, (name, n)
+        assert np.abs(np.linalg.eigvalsh(_band_dense(band, n)) - ev).max() <= 3e-14 * nrm, (name, n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [100, 300, 520, 1000])
+def test_svd_sym_two_stage_route(ctx, n, opt):
+    opt("TNAD_SYMEIG", "2")
+    opt("TNAD_EIG_2STAGE", "1")
+    rng = np.random.default_rng(n)
+    for name, a in _sym_cases(n, rng):
+        u, s, v = ctx.svd_sym(a)
+        ref = np.linalg.svd(a, compute_uv=False)
+        assert np.all(np.diff(s) <= 0)
+        assert np.abs(s - ref).max() <= 1e-12 * ref[0], name
+        assert np.abs((u * s) @ v.T - a).max() <= 1e-12 * ref[0], name
+        assert np.abs(u.T @ u - np.eye(n)).max() <= 1e-12, name
+
+
+@pytest.mark.gpu
+def test_energy_gradient_same_with_one_and_two_stage(ctx, opt):
+    """Energy + gradient must not depend on the tridiagonalisation route (chi D = 256)."""
+    rng = np.random.default_rng(6)
+    h = T.hamiltonian(T.Heisenberg())
+    A = T.indexperm_symmetrize(T.SquareIPEPS(rng.standard_normal((2, 2, 2, 2, 2)))).bulk
+    out = {}
+    for mode in ("0", "1"):
+        opt("TNAD_EIG_2STAGE", mode)
+        out[mode] = ctx.energy(h, A, 64, 0.0, 4, grad=True)
+    (e1, g1), (e2, g2) = out["0"], out["1"]
+    assert abs(e1 - e2) <= 1e-11 * abs(e1) and np.abs(g1 - g2).max() <= 1e-9 * np.abs(g1).max()
