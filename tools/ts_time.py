@@ -1,7 +1,7 @@
 """Stage timings of the symmetric eigensolver (TNAD_DC_DEBUG=1 prints them from the library).
 usage: ts_time.py n [two_stage 0|1] [reps]"""
 import os, sys
-os.environ["TNAD_DC_DEBUG"] = "1"
+os.environ.setdefault("TNAD_DC_DEBUG", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
