@@ -19,6 +19,7 @@
 #include "eigdc.h"
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <chrono>
 
 namespace cg = cooperative_groups;
 
@@ -132,240 +133,312 @@ struct ChaseArgs {
   double* V2;                    // (n-2) x ldv, zero-initialised
   long long ldv;
   double* tau2;                  // (n-2) x NP, zero-initialised
-  unsigned long long* gbox;      // NP x 2 x MB_WORDS, zero-initialised: [t][0] = reflector box, [t][1] = row box
+  unsigned long long* gbox;      // NP x 3 x MB_WORDS, zero-initialised: [t][0] = reflector box, [t][1..2] = row boxes
   int* err;
   long long* prof;               // optional: per position 6 cycle counters (wait row, wait v, E phase, D phase, sends, total)
 };
 
-// per-position shared memory (doubles): Ew (1 + 32*33 + 1), Dw (32*33), 6 scratch vectors of 34, two mailboxes
-constexpr int POS_DOUBLES = (2 + CB * WLD) + CB * WLD + 6 * 34 + 2 * MB_WORDS;
+// Two warps per position: the E warp owns the bulge block (right-apply the previous reflector, new reflector, column
+// sums, left-apply), the D warp the diagonal block (D <- H D H).  The reflector goes from the E warp to the D warp
+// through a local box; the D warp hands back the new last column of E (the old first column of D) and raises a flag.
+// per-position shared memory (doubles): Ew (1 + 32*33 + 1), Dw (32*33), 7 scratch vectors of 34, mailboxes:
+//   vbox (reflector from position t-1), rbox[2] (row from position t+1, double buffered by sweep parity: the D warp may
+//   lag the E warp by one hop), dbox (reflector E warp -> D warp), and a word the D warp uses to publish its progress
+constexpr int POS_BOXES = 4 * MB_WORDS + 2;
+constexpr int POS_DOUBLES = (2 + CB * WLD) + CB * WLD + 7 * 34 + POS_BOXES;
+constexpr int BOXOFF = POS_DOUBLES - POS_BOXES;      // offset of a position's boxes inside its shared-memory slice
+
+// the E warp needs double 0 of the row message only, the D warp doubles 1 .. 32 (lane l <-> double 1 + l)
+__device__ __forceinline__ bool mb_recv_one(unsigned long long* box, unsigned seq, int idx, double& out, int* err) {
+  volatile unsigned long long* vb = box;
+  unsigned long long w0, w1;
+  long long t0 = 0;
+  unsigned spins = 0;
+  for (;;) {
+    w0 = vb[2 * idx];
+    w1 = vb[2 * idx + 1];
+    const bool ok = (unsigned)(w0 >> 32) == seq && (unsigned)(w1 >> 32) == seq;
+    if (__all_sync(0xffffffffu, ok)) break;
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      const bool to = (now - t0 > 4000000000ll) || (*(volatile int*)err != 0);
+      if (__any_sync(0xffffffffu, to)) {
+        if ((threadIdx.x & 31) == 0) atomicExch(err, 1);
+        return false;
+      }
+    }
+  }
+  out = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return true;
+}
+__device__ __forceinline__ bool flag_wait(unsigned long long* word, unsigned long long want, int* err) {
+  volatile unsigned long long* vw = word;
+  long long t0 = 0;
+  unsigned spins = 0;
+  while (*vw < want) {
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if ((now - t0 > 4000000000ll) || (*(volatile int*)err != 0)) {
+        atomicExch(err, 1);
+        return false;
+      }
+    }
+  }
+  return true;
+}
 
 __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
   extern __shared__ double sm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int pw = wid >> 1;                        // position within the CTA
+  const bool is_d = (wid & 1) != 0;               // role: E warp / D warp
   // zero the local mailboxes of every position of this CTA before any neighbour may write into them
   for (int i = threadIdx.x; i < a.W * POS_DOUBLES; i += blockDim.x) sm[i] = 0.0;
   __syncthreads();
   cluster.sync();
-  const int t = blockIdx.x * a.W + wid;
+  const int t = blockIdx.x * a.W + pw;
   const int n = a.n;
   if (t < a.NP) {
-  double* base = sm + (size_t)wid * POS_DOUBLES;
+  double* base = sm + (size_t)pw * POS_DOUBLES;
   double* Ew = base + 1;                       // one double of head room: the shifted store of row 1 touches Ew[-1]
   double* Dw = base + 2 + CB * WLD;
-  double* sv = Dw + CB * WLD;                  // own reflector (34)
+  double* sv = Dw + CB * WLD;                  // own reflector, E warp's copy (34)
   double* svp = sv + 34;                       // previous reflector of the sweep + tau (34)
-  double* srow = svp + 34;                     // entering row (34)
-  double* sw = srow + 34;                      // E-phase coefficients w_k (34)
-  double* sd = sw + 34;                        // D-phase vector w (34)
-  double* stop = sd + 34;                      // leaving top row (34)
-  unsigned long long* lbox = reinterpret_cast<unsigned long long*>(stop + 34);   // [0] reflector box, [1] row box (local)
+  double* sw = svp + 34;                       // E-phase coefficients w_k (34)
+  double* stop = sw + 34;                      // leaving top row, E part (34)
+  double* svd = stop + 34;                     // own reflector + tau, D warp's copy (34)
+  double* sd = svd + 34;                       // D-phase vector w (34)
+  double* srow = sd + 34;                      // entering row, D part (34)
+  unsigned long long* lbox = reinterpret_cast<unsigned long long*>(base + BOXOFF);
+  unsigned long long* my_vbox_l = lbox;                         // reflector from t-1
+  unsigned long long* my_rbox_l = lbox + MB_WORDS;              // [2] row from t+1
+  unsigned long long* dbox = lbox + 3 * MB_WORDS;               // reflector E -> D
+  unsigned long long* dflag = lbox + 4 * MB_WORDS;              // D warp: number of hops whose E column is handed back
   // A mailbox lives with its READER: in the reader's shared memory when the writer sits in the same CTA or in the same
   // cluster (then the writer pushes through distributed shared memory), in global memory (L2) between clusters.
-  constexpr int BOXOFF = POS_DOUBLES - 2 * MB_WORDS;   // offset of a position's local boxes inside its shared-memory slice
-  const bool prev_cta = t > 0 && wid == 0, next_cta = t + 1 < a.NP && wid + 1 == a.W;
+  const bool prev_cta = t > 0 && pw == 0, next_cta = t + 1 < a.NP && pw + 1 == a.W;
   const bool prev_far = prev_cta && crank == 0, next_far = next_cta && crank + 1 == csize;   // neighbour in another cluster
-  unsigned long long* my_vbox = prev_far ? a.gbox + ((size_t)t * 2 + 0) * MB_WORDS : lbox;
-  unsigned long long* my_rbox = next_far ? a.gbox + ((size_t)t * 2 + 1) * MB_WORDS : lbox + MB_WORDS;
+  unsigned long long* my_vbox = prev_far ? a.gbox + ((size_t)t * 3 + 0) * MB_WORDS : my_vbox_l;
+  unsigned long long* my_rbox = next_far ? a.gbox + ((size_t)t * 3 + 1) * MB_WORDS : my_rbox_l;     // two consecutive boxes
   unsigned long long* nx_vbox;   // reflector box of position t+1
   if (!next_cta) nx_vbox = reinterpret_cast<unsigned long long*>(base + POS_DOUBLES + BOXOFF);
-  else if (next_far) nx_vbox = a.gbox + ((size_t)(t + 1) * 2 + 0) * MB_WORDS;
+  else if (next_far) nx_vbox = a.gbox + ((size_t)(t + 1) * 3 + 0) * MB_WORDS;
   else nx_vbox = reinterpret_cast<unsigned long long*>(cluster.map_shared_rank(sm + BOXOFF, crank + 1));
-  unsigned long long* pv_rbox;   // row box of position t-1
+  unsigned long long* pv_rbox;   // row boxes of position t-1
   if (!prev_cta) pv_rbox = reinterpret_cast<unsigned long long*>(base - POS_DOUBLES + BOXOFF) + MB_WORDS;
-  else if (prev_far) pv_rbox = a.gbox + ((size_t)(t > 0 ? t - 1 : 0) * 2 + 1) * MB_WORDS;
+  else if (prev_far) pv_rbox = a.gbox + ((size_t)(t > 0 ? t - 1 : 0) * 3 + 1) * MB_WORDS;
   else pv_rbox = reinterpret_cast<unsigned long long*>(cluster.map_shared_rank(sm + (size_t)(a.W - 1) * POS_DOUBLES + BOXOFF, crank - 1)) + MB_WORDS;
   const int my_sweeps = min(n - 2, n - 1 - CB * t);
   const int nx_sweeps = t + 1 < a.NP ? min(n - 2, n - 1 - CB * (t + 1)) : 0;
 
-  // ---- initial window (sweep 0): rows p .. p+31, p = 1 + 32 t; zero beyond the matrix ----
+  // ---- initial window (sweep 0): rows p .. p+31, p = 1 + 32 t; zero beyond the matrix (each warp loads its block) ----
   {
     const int p = 1 + CB * t;
     const int i = p + lane;   // my row
 #pragma unroll 4
     for (int k = 0; k < CB; ++k) {
-      double ev = 0.0, dv = 0.0;
+      double val = 0.0;
       if (i < n) {
-        const int je = p - CB + k;           // E column
-        if (t >= 1) {
-          if (i - je <= CB) ev = a.AB[(i - je) + (long long)je * a.ldab];
-        } else if (k == CB - 1) {
-          ev = a.AB[(i - 0) + 0];            // position 0: column 0, rows 1 .. 32
+        if (!is_d) {
+          const int je = p - CB + k;           // E column
+          if (t >= 1) {
+            if (i - je <= CB) val = a.AB[(i - je) + (long long)je * a.ldab];
+          } else if (k == CB - 1) {
+            val = a.AB[i];                     // position 0: column 0, rows 1 .. 32
+          }
+        } else {
+          const int jd = p + k;                // D column
+          if (jd < n) val = (i >= jd) ? a.AB[(i - jd) + (long long)jd * a.ldab] : a.AB[(jd - i) + (long long)i * a.ldab];
         }
-        const int jd = p + k;                // D column
-        if (jd < n) dv = (i >= jd) ? a.AB[(i - jd) + (long long)jd * a.ldab] : a.AB[(jd - i) + (long long)i * a.ldab];
       }
-      Ew[lane * WLD + k] = ev;
-      Dw[lane * WLD + k] = dv;
+      (is_d ? Dw : Ew)[lane * WLD + k] = val;
     }
-    if (t == 0 && lane == 0) a.d[0] = a.AB[0];
-    __syncwarp();
+    if (t == 0 && lane == 0 && !is_d) a.d[0] = a.AB[0];
   }
+  // both warps of the position have written their block (named barrier: 64 threads)
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + pw) : "memory");
 
-  double Dlast0 = 0.0, Dlast1 = 0.0;   // D[1][0], D[1][1] of position 0 after its last hop
   long long pc[6] = {0, 0, 0, 0, 0, 0};
   const bool prof = a.prof != nullptr;
   const long long tstart = prof ? clock64() : 0;
-  for (int s = 0; s < my_sweeps; ++s) {
-    const unsigned seq = (unsigned)s + 1u;
-    long long tk = prof ? clock64() : 0;
 #define CH_TICK(slot)                     \
     if (prof) {                           \
       const long long _n = clock64();     \
       pc[slot] += _n - tk;                \
       tk = _n;                            \
     }
-    // ---- entering row (from position t+1, produced at sweep s-1) ----
-    const bool have_row = s > 0;
-    if (have_row) {
-      if (s - 1 < nx_sweeps) {
-        if (!mb_recv(my_rbox, (unsigned)s, srow, lane, a.err)) break;
+  if (!is_d) {
+    // =============================================== E warp ===============================================
+    for (int s = 0; s < my_sweeps; ++s) {
+      const unsigned seq = (unsigned)s + 1u;
+      long long tk = prof ? clock64() : 0;
+      // the D warp has handed back column 31 of my block for this sweep (its hop s-1)
+      if (s > 0 && !flag_wait(dflag, (unsigned long long)s, a.err)) break;
+      __threadfence_block();                     // acquire: the column the D warp stored before raising the flag
+      double ent = 0.0;                          // E'[31][31]: double 0 of the row that enters from position t+1
+      if (s > 0 && s - 1 < nx_sweeps) {
+        if (!mb_recv_one(my_rbox + ((s - 1) & 1) * MB_WORDS, (unsigned)s, 0, ent, a.err)) break;
+      }
+      CH_TICK(0)
+      double v, tau, beta;
+      double Er[CB];
+      if (t == 0) {
+        double x = Ew[lane * WLD + (CB - 1)];
+        if (s > 0 && lane == CB - 1) x = ent;
+        v = warp_house(x, lane, tau, beta);
+        if (lane == 0) a.e[s] = beta;
       } else {
-        srow[lane] = 0.0;
-        if (lane == 0) srow[CB] = 0.0;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) Er[k] = Ew[lane * WLD + k];
+        if (s > 0 && lane == CB - 1) {
+#pragma unroll
+          for (int k = 0; k < CB - 1; ++k) Er[k] = 0.0;
+          Er[CB - 1] = ent;
+        }
+        CH_TICK(2)
+        if (!mb_recv(my_vbox, seq, svp, lane, a.err)) break;
+        CH_TICK(1)
+        {
+          const double taup = svp[CB];
+          double dot0 = 0.0, dot1 = 0.0, dot2 = 0.0, dot3 = 0.0;
+#pragma unroll
+          for (int k = 0; k < CB; k += 4) {
+            dot0 = fma(Er[k], svp[k], dot0);
+            dot1 = fma(Er[k + 1], svp[k + 1], dot1);
+            dot2 = fma(Er[k + 2], svp[k + 2], dot2);
+            dot3 = fma(Er[k + 3], svp[k + 3], dot3);
+          }
+          const double f = taup * ((dot0 + dot1) + (dot2 + dot3));
+#pragma unroll
+          for (int k = 0; k < CB; ++k) Er[k] = fma(-f, svp[k], Er[k]);
+        }
+        v = warp_house(Er[0], lane, tau, beta);
+      }
+      // reflector out at once: to my D warp and to position t+1
+      mb_send(dbox, seq, lane, v);
+      if (lane == 0) mb_send(dbox, seq, CB, tau);
+      if (s < nx_sweeps) {
+        mb_send(nx_vbox, seq, lane, v);
+        if (lane == 0) mb_send(nx_vbox, seq, CB, tau);
+      }
+      if (t > 0) {
+        double val[CB];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) val[k] = v * Er[k];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int k = 0; k < o; ++k) {
+            const double snd = up ? val[k] : val[k + o];
+            const double keep = up ? val[k + o] : val[k];
+            val[k] = keep + __shfl_xor_sync(0xffffffffu, snd, o);
+          }
+        }
+        sw[lane] = lane == 0 ? 0.0 : tau * val[0];
         __syncwarp();
+        // left-apply and store the block of the next sweep shifted by (1,1); row 0 (v_0 = 1) is the E part of the row
+        // that leaves to position t-1: lane 0 stores it to the send buffer with the same instructions
+        {
+          double wk[CB];                             // all loads first: the stores below may alias sw for the compiler
+#pragma unroll
+          for (int k = 1; k < CB; ++k) wk[k] = sw[k];
+          double* dst = lane == 0 ? stop : Ew + (lane - 1) * WLD - 1;
+#pragma unroll
+          for (int k = 1; k < CB; ++k) dst[k] = fma(-v, wk[k], Er[k]);     // column 0 is annihilated: not stored
+          if (lane == 0) stop[0] = beta;
+        }
+        __syncwarp();
+        CH_TICK(2)
+        mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, lane, stop[lane]);
+        CH_TICK(4)
       }
+      a.V2[(long long)s * a.ldv + CB * t + lane] = v;
+      if (lane == 0) a.tau2[(long long)s * a.NP + t] = tau;
+      __syncwarp();
+      CH_TICK(3)
     }
-    CH_TICK(0)
-    // ---- E phase: everything the neighbours wait for comes first ----
-    double v, tau, beta;
-    double Er[CB];
-    if (t == 0) {
-      double x = Ew[lane * WLD + (CB - 1)];
-      if (have_row && lane == CB - 1) x = srow[0];
-      v = warp_house(x, lane, tau, beta);
-      if (lane == 0) a.e[s] = beta;
-    } else {
+  } else {
+    // =============================================== D warp ===============================================
+    double Dlast0 = 0.0, Dlast1 = 0.0;   // D[1][0], D[1][1] of position 0 after its last hop
+    for (int s = 0; s < my_sweeps; ++s) {
+      const unsigned seq = (unsigned)s + 1u;
+      long long tk = prof ? clock64() : 0;
+      double Dc[CB];
 #pragma unroll
-      for (int k = 0; k < CB; ++k) Er[k] = Ew[lane * WLD + k];
-      if (have_row && lane == CB - 1) {
+      for (int i = 0; i < CB; ++i) Dc[i] = Dw[lane * WLD + i];
+      if (s > 0) {
+        double mine = 0.0;                       // double 1 + lane of the entering row
+        if (s - 1 < nx_sweeps) {
+          if (!mb_recv_one(my_rbox + ((s - 1) & 1) * MB_WORDS, (unsigned)s, 1 + lane, mine, a.err)) break;
+        }
+        srow[lane] = mine;
+        __syncwarp();
+        if (lane == CB - 1) {
 #pragma unroll
-        for (int k = 0; k < CB - 1; ++k) Er[k] = 0.0;
-        Er[CB - 1] = srow[0];
+          for (int i = 0; i < CB; ++i) Dc[i] = srow[i];
+        } else {
+          Dc[CB - 1] = mine;
+        }
       }
-      // (a) right-apply the previous reflector of this sweep
-      CH_TICK(2)
-      if (!mb_recv(my_vbox, seq, svp, lane, a.err)) break;
+      CH_TICK(0)
+      if (!mb_recv(dbox, seq, svd, lane, a.err)) break;
       CH_TICK(1)
-      {
-        const double taup = svp[CB];
-        double dot0 = 0.0, dot1 = 0.0, dot2 = 0.0, dot3 = 0.0;
-#pragma unroll
-        for (int k = 0; k < CB; k += 4) {
-          dot0 = fma(Er[k], svp[k], dot0);
-          dot1 = fma(Er[k + 1], svp[k + 1], dot1);
-          dot2 = fma(Er[k + 2], svp[k + 2], dot2);
-          dot3 = fma(Er[k + 3], svp[k + 3], dot3);
-        }
-        const double f = taup * ((dot0 + dot1) + (dot2 + dot3));
-#pragma unroll
-        for (int k = 0; k < CB; ++k) Er[k] = fma(-f, svp[k], Er[k]);
-      }
-      // (b) reflector that annihilates the first column of the bulge
-      v = warp_house(Er[0], lane, tau, beta);
-    }
-    // reflector out at once: position t+1 is waiting for it
-    sv[lane] = v;
-    if (s < nx_sweeps) {
-      mb_send(nx_vbox, seq, lane, v);
-      if (lane == 0) mb_send(nx_vbox, seq, CB, tau);
-    }
-    if (t > 0) {
-      // (c) column sums c_k = sum_rows v_r E[r][k] by recursive halving: lane k ends up with c_k
-      double val[CB];
-#pragma unroll
-      for (int k = 0; k < CB; ++k) val[k] = v * Er[k];
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int k = 0; k < o; ++k) {
-          const double snd = up ? val[k] : val[k + o];
-          const double keep = up ? val[k + o] : val[k];
-          val[k] = keep + __shfl_xor_sync(0xffffffffu, snd, o);
-        }
-      }
-      sw[lane] = lane == 0 ? 0.0 : tau * val[0];
-    }
-    __syncwarp();
-    CH_TICK(2)
-    // ---- D phase, first half: w = tau D v - (tau^2 / 2)(v' D v) v ----
-    double Dc[CB];
-#pragma unroll
-    for (int i = 0; i < CB; ++i) Dc[i] = Dw[lane * WLD + i];
-    if (have_row) {
-      if (lane == CB - 1) {
-#pragma unroll
-        for (int i = 0; i < CB; ++i) Dc[i] = srow[1 + i];
-      } else {
-        Dc[CB - 1] = srow[1 + lane];
-      }
-    }
-    double wd;
-    {
+      const double v = svd[lane], tau = svd[CB];
       double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
 #pragma unroll
       for (int i = 0; i < CB; i += 4) {
-        y0 = fma(Dc[i], sv[i], y0);
-        y1 = fma(Dc[i + 1], sv[i + 1], y1);
-        y2 = fma(Dc[i + 2], sv[i + 2], y2);
-        y3 = fma(Dc[i + 3], sv[i + 3], y3);
+        y0 = fma(Dc[i], svd[i], y0);
+        y1 = fma(Dc[i + 1], svd[i + 1], y1);
+        y2 = fma(Dc[i + 2], svd[i + 2], y2);
+        y3 = fma(Dc[i + 3], svd[i + 3], y3);
       }
-      wd = tau * ((y0 + y1) + (y2 + y3));
+      double wd = tau * ((y0 + y1) + (y2 + y3));
       const double gamma = wsum(wd * v);
       wd = fma(-0.5 * tau * gamma, v, wd);
       sd[lane] = wd;
-    }
-    // the row that leaves to position t-1 (v_0 = 1): E[0][k] - w_k, D[0][0] - 2 wd_0
-    if (lane == 0) {
-      if (t > 0) {
-        stop[0] = beta;
-#pragma unroll
-        for (int k = 1; k < CB; ++k) stop[k] = Er[k] - sw[k];
+      __syncwarp();
+      // row 0 / column 0 of the updated block first: D[0][0] leaves to position t-1, D[0][1..31] becomes the new last
+      // column of E (handed back to the E warp)
+      Dc[0] -= svd[0] * wd + sd[0] * v;
+      if (lane == 0) {
+        if (t > 0) mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, CB, Dc[0]);
+        else a.d[s + 1] = Dc[0];
+      } else {
+        Ew[(lane - 1) * WLD + (CB - 1)] = Dc[0];
       }
-      const double d00 = Dc[0] - 2.0 * wd;
-      stop[CB] = d00;
-      if (t == 0) a.d[s + 1] = d00;
-    }
-    __syncwarp();
-    CH_TICK(3)
-    if (t > 0) {
-      mb_send(pv_rbox, seq, lane, stop[lane]);
-      if (lane == 0) mb_send(pv_rbox, seq, CB, stop[CB]);
-    }
-    CH_TICK(4)
-    // ---- off the critical path: reflector store, bulk updates, windows of the next sweep (shifted by (1,1)) ----
-    a.V2[(long long)s * a.ldv + CB * t + lane] = v;
-    if (lane == 0) a.tau2[(long long)s * a.NP + t] = tau;
-    if (t > 0 && lane >= 1) {
-      double* dst = Ew + (lane - 1) * WLD - 1;
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        *(volatile unsigned long long*)dflag = (unsigned long long)(s + 1);
+      }
+      CH_TICK(3)
 #pragma unroll
-      for (int k = 1; k < CB; ++k) dst[k] = fma(-v, sw[k], Er[k]);     // column 0 is annihilated: not stored
-    }
+      for (int i = 1; i < CB; ++i) Dc[i] -= svd[i] * wd + sd[i] * v;
+      if (lane >= 1) {
+        double* dd = Dw + (lane - 1) * WLD - 1;
 #pragma unroll
-    for (int i = 0; i < CB; ++i) Dc[i] -= sv[i] * wd + sd[i] * v;
-    if (lane >= 1) {
-      double* dd = Dw + (lane - 1) * WLD - 1;
-#pragma unroll
-      for (int i = 1; i < CB; ++i) dd[i] = Dc[i];
-      Ew[(lane - 1) * WLD + (CB - 1)] = Dc[0];      // the new last column of E is the old first column of D
+        for (int i = 1; i < CB; ++i) dd[i] = Dc[i];
+      }
+      if (t == 0 && s == my_sweeps - 1 && lane == 1) {
+        Dlast0 = Dc[0];
+        Dlast1 = Dc[1];
+      }
+      __syncwarp();
+      CH_TICK(4)
     }
-    if (t == 0 && s == my_sweeps - 1 && lane == 1) {
-      Dlast0 = Dc[0];
-      Dlast1 = Dc[1];
+    if (t == 0 && lane == 1 && n >= 3) {
+      a.d[n - 1] = Dlast1;
+      a.e[n - 2] = Dlast0;
     }
-    __syncwarp();
-    CH_TICK(3)
   }
   if (prof && lane == 0) {
     pc[5] = clock64() - tstart;
-    for (int i = 0; i < 6; ++i) a.prof[(long long)t * 6 + i] = pc[i];
-  }
-  if (t == 0 && lane == 1 && n >= 3) {
-    a.d[n - 1] = Dlast1;
-    a.e[n - 2] = Dlast0;
+    for (int i = 0; i < 6; ++i) a.prof[((long long)t * 2 + (is_d ? 1 : 0)) * 6 + i] = pc[i];
   }
   }   // t < NP
   cluster.sync();   // no CTA may exit while a neighbour can still push into its mailboxes
@@ -380,8 +453,9 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
 // from slot q-1 of the same CTA through shared memory, for the first slot of the stage from the stream the previous
 // stage wrote (for stage 0: from X itself); the bottom row leaves to slot q+1 / to the stream of the next stage.
 constexpr int QS = 32;          // slots per stage (CTA)
-constexpr int QC = 16;          // columns per CTA (one per thread, 16 threads per slot)
-constexpr int Q2_NT = QS * QC;  // 512 threads
+constexpr int QC = 16;          // columns per CTA
+constexpr int QH = 16;          // rows per thread: a slot's 32-row window is split over two threads (upper / lower half)
+constexpr int Q2_NT = QS * 2 * (QC / 2);   // 512 threads: (slot, half, column pair)
 
 struct Q2Args {
   double* X;                    // n_rows x ncols, leading dimension ldx (rows >= n are not touched)
@@ -398,25 +472,30 @@ struct Q2Args {
   int s_top;                    // first (largest) sweep index processed; s_top + 1 is a multiple of 32
 };
 
+// Thread = (slot, half, column pair): 16 rows of 2 columns in registers, its half of the reflector cached in registers for
+// both passes (dot, update): 2 bytes of shared-memory traffic per FMA (the load/store unit moves 128 B/clk/SM, the FP64
+// pipe executes 64 FMA/clk/SM).  The two halves of a slot sit in lanes l and l ^ 8: one shuffle combines the dots, one
+// hands the row that crosses the middle of the window.
 __global__ void __launch_bounds__(Q2_NT, 1) k_q2_stage(const Q2Args a) {
   constexpr int NB = 4;                           // ring of reflector buffers: prefetch distance 3 sweeps
   constexpr int UNR = 4;                          // sweeps per physical register shift
   __shared__ double vbuf[NB][QS * CB];            // the reflectors of the stage's slots for one sweep (8 KB each)
   __shared__ double tbuf[NB][QS];                 // their taus
   __shared__ double xfer[2][QS][QC];              // bottom rows handed to the next slot
-  const int tid = threadIdx.x;
-  const int sl = tid >> 4;                        // slot within the stage (a warp holds two slots)
-  const int cl = tid & 15;                        // column within the CTA
+  __shared__ double topbuf[NB][QC];               // rows entering the first slot of the stage (from the stream / the matrix)
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int sl = wid * 2 + (lane >> 4);           // slot within the stage
+  const int h = (lane >> 3) & 1;                  // 0: rows 0..15 of the window, 1: rows 16..31
+  const int cp = lane & 7;                        // column pair
   const int q = a.q0 + sl;
-  const int c0 = blockIdx.x * QC + cl;
-  const bool ok0 = c0 < a.ncols;
+  const int c0 = blockIdx.x * QC + 2 * cp, c1 = c0 + 1;
+  const bool ok0 = c0 < a.ncols, ok1 = c1 < a.ncols;
   const int n = a.n;
-  // window registers: at sub-step r of a block of UNR sweeps the logical row k lives in x[k + UNR - 1 - r]; every UNR
-  // sweeps the registers are shifted up by UNR (a fully static circular buffer would need the loop unrolled 32 times,
-  // which does not fit the instruction cache)
-  double x0[CB + UNR];
+  // at sub-step r of a block of UNR sweeps the logical row k of my half lives in x[k + UNR - 1 - r]; every UNR sweeps the
+  // registers are shifted up by UNR (a fully static circular buffer would need the sweep loop unrolled 32 times)
+  double x0[QH + UNR], x1[QH + UNR];
 #pragma unroll
-  for (int k = 0; k < CB + UNR; ++k) x0[k] = 0.0;
+  for (int k = 0; k < QH + UNR; ++k) x0[k] = x1[k] = 0.0;
   for (int i = tid; i < 2 * QS * QC; i += Q2_NT) (&xfer[0][0][0])[i] = 0.0;
 
   auto stage_v = [&](int s, int buf) {   // cp.async the 32 x 32 reflector block of sweep s (nothing for sweeps without reflectors)
@@ -442,22 +521,29 @@ __global__ void __launch_bounds__(Q2_NT, 1) k_q2_stage(const Q2Args a) {
         tbuf[buf][tid] = 0.0;
       }
     }
+    // the row that enters the first slot of the stage at sweep s (row s + 1 of the matrix for stage 0)
+    if (tid >= 64 && tid < 64 + QC) {
+      const int cc = tid - 64, col = blockIdx.x * QC + cc;
+      const double* src = nullptr;
+      if (s >= 0 && col < a.ncols) {
+        if (a.sin) {
+          if (s <= n - 2) src = a.sin + (long long)s * a.lds + col;
+        } else if (s + 1 < n) {
+          src = a.X + (s + 1) + (long long)col * a.ldx;
+        }
+      }
+      if (src) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(&topbuf[buf][cc]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
+      } else {
+        topbuf[buf][cc] = 0.0;
+      }
+    }
     asm volatile("cp.async.commit_group;\n" ::);
   };
-  // entering rows of the first slot of the stage come from global memory: fetched three steps ahead
-  auto fetch_top = [&](int s) -> double {
-    if (sl != 0 || s < 0 || !ok0) return 0.0;
-    if (a.sin) return s <= n - 2 ? a.sin[(long long)s * a.lds + c0] : 0.0;
-    return s + 1 < n ? a.X[(s + 1) + (long long)c0 * a.ldx] : 0.0;
-  };
 
-  double pre0[NB];
 #pragma unroll
-  for (int i = 0; i < NB - 1; ++i) {
-    stage_v(a.s_top - i, i);
-    pre0[i] = fetch_top(a.s_top - i);
-  }
-  pre0[NB - 1] = 0.0;
+  for (int i = 0; i < NB - 1; ++i) stage_v(a.s_top - i, i);
   int par = 0;
   for (int sb = a.s_top; sb >= 0; sb -= UNR) {
 #pragma unroll
@@ -467,53 +553,79 @@ __global__ void __launch_bounds__(Q2_NT, 1) k_q2_stage(const Q2Args a) {
       asm volatile("cp.async.wait_group %0;\n" ::"n"(NB - 2));
       __syncthreads();                               // vbuf[buf], tbuf[buf] and xfer[par] (written in the previous step) are visible;
       stage_v(s - (NB - 1), (r + NB - 1) % NB);      // every warp has left the previous step: its buffer may be refilled
-      // entering row p = s + 1 + 32 q
-      double e0;
-      if (sl == 0) {
-        e0 = pre0[r];
-        pre0[(r + NB - 1) % NB] = fetch_top(s - (NB - 1));
-      } else {
-        e0 = xfer[par][sl - 1][cl];
+      const int off = UNR - 1 - r;                   // logical row k of my half <-> register k + off
+      // slide the window up by one row: the row that leaves my half sits in register QH + off
+      const double up0 = __shfl_xor_sync(0xffffffffu, x0[QH + off], 8);
+      const double up1 = __shfl_xor_sync(0xffffffffu, x1[QH + off], 8);
+      double e0, e1;
+      if (h == 1) {                                  // from the upper half of the same slot
+        e0 = up0;
+        e1 = up1;
+      } else if (sl == 0) {                          // from the previous stage / the matrix
+        e0 = topbuf[buf][2 * cp];
+        e1 = topbuf[buf][2 * cp + 1];
+      } else {                                       // from the slot above
+        e0 = xfer[par][sl - 1][2 * cp];
+        e1 = xfer[par][sl - 1][2 * cp + 1];
       }
-      const int off = UNR - 1 - r;                   // logical row k <-> register k + off
       x0[off] = e0;
+      x1[off] = e1;
       const double tau = tbuf[buf][sl];
-      if (tau != 0.0) {
-        const double* vv = vbuf[buf] + sl * CB;
+      if (tau != 0.0) {                              // uniform over the 16 lanes of a slot
+        const double* vv = vbuf[buf] + sl * CB + h * QH;
+        double vh[QH];
+#pragma unroll
+        for (int k = 0; k < QH; k += 2) {
+          const double2 v2 = *reinterpret_cast<const double2*>(vv + k);
+          vh[k] = v2.x;
+          vh[k + 1] = v2.y;
+        }
         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-        for (int k = 0; k < CB; k += 4) {
-          const double2 va = *reinterpret_cast<const double2*>(vv + k);
-          const double2 vb = *reinterpret_cast<const double2*>(vv + k + 2);
-          d0 = fma(va.x, x0[k + off], d0);
-          d1 = fma(va.y, x0[k + 1 + off], d1);
-          d2 = fma(vb.x, x0[k + 2 + off], d2);
-          d3 = fma(vb.y, x0[k + 3 + off], d3);
+        for (int k = 0; k < QH; k += 2) {
+          d0 = fma(vh[k], x0[k + off], d0);
+          d1 = fma(vh[k], x1[k + off], d1);
+          d2 = fma(vh[k + 1], x0[k + 1 + off], d2);
+          d3 = fma(vh[k + 1], x1[k + 1 + off], d3);
         }
-        const double f0 = -tau * ((d0 + d1) + (d2 + d3));
+        d0 += d2;
+        d1 += d3;
+        d0 += __shfl_xor_sync(0x0000ffffu << (lane & 16), d0, 8);
+        d1 += __shfl_xor_sync(0x0000ffffu << (lane & 16), d1, 8);
+        const double f0 = -tau * d0, f1 = -tau * d1;
 #pragma unroll
-        for (int k = 0; k < CB; k += 2) {
-          const double2 v2 = *reinterpret_cast<const double2*>(vv + k);
-          x0[k + off] = fma(f0, v2.x, x0[k + off]);
-          x0[k + 1 + off] = fma(f0, v2.y, x0[k + 1 + off]);
+        for (int k = 0; k < QH; ++k) {
+          x0[k + off] = fma(f0, vh[k], x0[k + off]);
+          x1[k + off] = fma(f1, vh[k], x1[k + off]);
         }
       }
-      // the bottom row (logical 31) leaves at the next slide
-      const double b0 = x0[CB - 1 + off];
-      xfer[par ^ 1][sl][cl] = b0;
-      if (sl == QS - 1 && a.sout && s >= 1 && ok0) a.sout[(long long)(s - 1) * a.lds + c0] = b0;
+      // the bottom row of the window (lower half, logical row 15 of that half) leaves the slot at the next slide
+      if (h == 1) {
+        const double b0 = x0[QH - 1 + off], b1 = x1[QH - 1 + off];
+        xfer[par ^ 1][sl][2 * cp] = b0;
+        xfer[par ^ 1][sl][2 * cp + 1] = b1;
+        if (sl == QS - 1 && a.sout && s >= 1) {
+          if (ok0) a.sout[(long long)(s - 1) * a.lds + c0] = b0;
+          if (ok1) a.sout[(long long)(s - 1) * a.lds + c1] = b1;
+        }
+      }
       par ^= 1;
     }
     // after UNR sweeps logical row k sits in register k: move everything up by UNR for the next block
 #pragma unroll
-    for (int k = CB - 1; k >= 0; --k) x0[k + UNR] = x0[k];
+    for (int k = QH - 1; k >= 0; --k) {
+      x0[k + UNR] = x0[k];
+      x1[k + UNR] = x1[k];
+    }
   }
-  // final windows (state after sweep 0, already shifted: logical row k in register k + UNR), rows 1 + 32 q ..
-  const int p = 1 + CB * q;
-  if (ok0) {
+  // final windows (state after sweep 0, already shifted: logical row k in register k + UNR), rows 1 + 32 q + 16 h ..
+  const int p = 1 + CB * q + QH * h;
 #pragma unroll
-    for (int k = 0; k < CB; ++k)
-      if (p + k < n) a.X[(p + k) + (long long)c0 * a.ldx] = x0[k + UNR];
+  for (int k = 0; k < QH; ++k) {
+    if (p + k < n) {
+      if (ok0) a.X[(p + k) + (long long)c0 * a.ldx] = x0[k + UNR];
+      if (ok1) a.X[(p + k) + (long long)c1 * a.ldx] = x1[k + UNR];
+    }
   }
 }
 
@@ -539,8 +651,259 @@ struct PanelArgs {
   double* tau;        // tau[j + k]
   double* T;          // 32 x 32 compact-WY factor of this panel (column-major)
   long long* prof;    // optional: 8 cycle counters (rank 0, thread 0)
+  const int* only_if; // optional: run only when *only_if != 0 (the Gram-based kernel asked for the fallback)
 };
 
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cpa8(double* sdst, const double* g, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cpa16(double* sdst, const double* g, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(sz) : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path of the panel factorisation: Householder QR driven by the Gram matrix.
+//   G = P'P (full columns) is invariant under the reflectors, so the dot products over the rows BELOW the pivot that
+//   Householder needs at column c are  g_ck = G[c][k] - sum_{r<c} R[r][c] R[r][k] - P[c][c] P[c][k]  -- they follow from
+//   G and from the top 32 x 32 block of the panel alone.  Every CTA holds both (one cluster-wide reduction of the 32 x 32
+//   partial Gram matrices at the start), so the whole sequence of reflector scalars and update coefficients is computed
+//   by warp 0 of every CTA redundantly, without any further exchange, and the rows are then transformed independently.
+//   The subtraction cancels when column c lies (almost) in the span of the previous ones: if the remaining part carries
+//   less than PQ_THETA of the column's squared norm the panel is handed to the exchange-per-column kernel (k_panel_qr),
+//   which recomputes every dot product from the data (flag *fb = 1; nothing has been written at that point).
+//   T comes from the Gram matrix of the finished reflectors (second reduction), as in dlarft.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr double PQ_THETA = 0.0625;
+constexpr int PG_LDS = 33;
+template <int NRL>
+__global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int* fb) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();   // CS is a power of two <= 16
+  extern __shared__ double sm[];
+  constexpr int ROWS = PQ_NT * NRL, LDR = ROWS + 4;
+  double* Ys = sm;                               // [32][LDR] column-major copy of my rows (DMMA operand)
+  double* Gl = Ys + (size_t)CB * LDR;            // [32][33] local partial Gram
+  double* recv = Gl + CB * PG_LDS;               // [CS][RS * 32] slices received from the other CTAs (1024 doubles)
+  double* Gs = recv + CB * CB;                   // [32][33] full Gram
+  double* tops = Gs + CB * PG_LDS;               // [32][33] top block of the panel (rows 0..31), updated in place
+  double* Rs = tops + CB * PG_LDS;               // [32][33] finished rows of R
+  double* wtab = Rs + CB * PG_LDS;               // [32][32] update coefficients per column
+  double* sctab = wtab + CB * CB;                // [32] scale
+  double* betab = sctab + CB;                    // [32] beta
+  double* tautab = betab + CB;                   // [32] tau
+  double* sT = tautab + CB;                      // [32][32]
+  int* flag = reinterpret_cast<int*>(sT + CB * CB);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int r0 = a.j + CB, m = a.n - r0;
+  const int rp = a.rp;                           // == ROWS
+  const int row_lo = rank * rp;
+  const int nr = max(0, min(m, row_lo + rp) - row_lo);
+  const int RS = CB / CS;                        // Gram rows owned by each rank in the reduction
+  double pr[NRL][CB];
+#pragma unroll
+  for (int i = 0; i < NRL; ++i) {
+    const int r = i * PQ_NT + tid;
+    const double* src = a.A + (r0 + row_lo + r) + (long long)a.j * a.lda;
+#pragma unroll
+    for (int k = 0; k < CB; ++k) pr[i][k] = r < nr ? src[(long long)k * a.lda] : 0.0;
+  }
+  if (tid == 0) *flag = 0;
+
+  // Gram matrix of the rows staged in Ys: warp w computes the 8 x 8 tiles (w >> 1, 2 (w & 1) + {0, 1}) over all rows
+  auto gram_local = [&]() {
+    const int I = wid >> 1, J0 = 2 * (wid & 1);
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    const double* pa = Ys + (size_t)(8 * I + g8) * LDR + t4;
+    const double* pb0 = Ys + (size_t)(8 * J0 + g8) * LDR + t4;
+    const double* pb1 = pb0 + (size_t)8 * LDR;
+#pragma unroll 4
+    for (int q = 0; q < ROWS / 4; ++q) {
+      const double av = pa[4 * q], b0 = pb0[4 * q], b1 = pb1[4 * q];
+      dmma884(c00, c01, av, b0);
+      dmma884(c10, c11, av, b1);
+    }
+    Gl[(8 * I + g8) * PG_LDS + 8 * J0 + 2 * t4] = c00;
+    Gl[(8 * I + g8) * PG_LDS + 8 * J0 + 2 * t4 + 1] = c01;
+    Gl[(8 * I + g8) * PG_LDS + 8 * (J0 + 1) + 2 * t4] = c10;
+    Gl[(8 * I + g8) * PG_LDS + 8 * (J0 + 1) + 2 * t4 + 1] = c11;
+  };
+  // cluster-wide sum of the local Gram matrices (fixed order): rank d reduces rows d RS .. and broadcasts them
+  auto gram_reduce = [&]() {
+    __syncthreads();
+    if (CS == 1) {
+      for (int idx = tid; idx < CB * CB; idx += PQ_NT) Gs[(idx >> 5) * PG_LDS + (idx & 31)] = Gl[(idx >> 5) * PG_LDS + (idx & 31)];
+      __syncthreads();
+      return;
+    }
+    for (int idx = tid; idx < CB * CB; idx += PQ_NT) {
+      const int row = idx >> 5, col = idx & 31;
+      const int dstr = row / RS;
+      cluster.map_shared_rank(recv, dstr)[rank * (RS * CB) + (row - dstr * RS) * CB + col] = Gl[row * PG_LDS + col];
+    }
+    cluster.sync();
+    for (int idx = tid; idx < RS * CB; idx += PQ_NT) {
+      double sum = 0.0;
+      for (int src = 0; src < CS; ++src) sum += recv[src * (RS * CB) + idx];
+      const int row = rank * RS + idx / CB, col = idx % CB;
+      for (int dsti = 0; dsti < CS; ++dsti) cluster.map_shared_rank(Gs, dsti)[row * PG_LDS + col] = sum;
+    }
+    cluster.sync();
+  };
+
+  // ---- phase 1: G = P'P, top block to everybody ----
+#pragma unroll
+  for (int i = 0; i < NRL; ++i)
+#pragma unroll
+    for (int k = 0; k < CB; ++k) Ys[(size_t)k * LDR + i * PQ_NT + tid] = pr[i][k];
+  if (rank == 0 && tid < CB) {
+    for (int dsti = 0; dsti < CS; ++dsti) {
+      double* tp = cluster.map_shared_rank(tops, dsti);
+#pragma unroll
+      for (int k = 0; k < CB; ++k) tp[tid * PG_LDS + k] = pr[0][k];
+    }
+  }
+  __syncthreads();
+  gram_local();
+  gram_reduce();   // its cluster barriers also publish the top block
+  if (CS == 1) __syncthreads();
+
+  // ---- phase 2: the table of reflector scalars and update coefficients (warp 0, lane k <-> column k) ----
+  if (wid == 0) {
+    int bad = 0;
+    double tc[CB];                                 // column `lane` of the top block, updated in registers
+#pragma unroll
+    for (int r = 0; r < CB; ++r) tc[r] = tops[r * PG_LDS + lane];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // sum_{r<c} R[r][c] R[r][k]
+#pragma unroll
+      for (int r = 0; r < c; ++r) {
+        const double rc = Rs[r * PG_LDS + c], rk = Rs[r * PG_LDS + lane];
+        if ((r & 3) == 0) s0 = fma(rc, rk, s0);
+        else if ((r & 3) == 1) s1 = fma(rc, rk, s1);
+        else if ((r & 3) == 2) s2 = fma(rc, rk, s2);
+        else s3 = fma(rc, rk, s3);
+      }
+      const double ssum = (s0 + s1) + (s2 + s3);
+      const double pk = tc[c];
+      const double alpha = __shfl_sync(0xffffffffu, pk, c);
+      const double gk = Gs[c * PG_LDS + lane] - ssum - alpha * pk;
+      const double xn2 = __shfl_sync(0xffffffffu, gk, c);
+      const double gcc = Gs[c * PG_LDS + c];
+      double tau = 0.0, beta = alpha, scale = 0.0;
+      if (!(xn2 >= PQ_THETA * gcc) && gcc > 0.0) bad = 1;     // cancellation (or a NaN): let the exchange kernel redo the panel
+      if (xn2 > 0.0) {
+        const double sq = fma(alpha, alpha, xn2);
+        const double rn = rsqrt(sq);
+        const double nrm = sq * rn, aa = fabs(alpha);
+        beta = alpha >= 0.0 ? -nrm : nrm;
+        tau = fma(aa, rn, 1.0);
+        const double rcp = 1.0 / (aa + nrm);
+        scale = alpha >= 0.0 ? rcp : -rcp;
+      }
+      const double w = lane > c ? tau * (pk + scale * gk) : 0.0;
+      wtab[c * CB + lane] = w;
+      if (lane == c) {
+        sctab[c] = scale;
+        betab[c] = beta;
+        tautab[c] = tau;
+      }
+      // finished row c of R; rows c+1.. of the top block get the reflector (v_r = scale * column c of the block)
+      Rs[c * PG_LDS + lane] = lane > c ? pk - w : (lane == c ? beta : 0.0);
+#pragma unroll
+      for (int r = c + 1; r < CB; ++r) {
+        const double vr = scale * __shfl_sync(0xffffffffu, tc[r], c);
+        tc[r] = fma(-vr, w, tc[r]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) *flag = bad;
+  }
+  __syncthreads();
+  if (*flag) {                                    // uniform over the cluster: every CTA computed the same table
+    if (rank == 0 && tid == 0) *fb = 1;
+    cluster.sync();
+    return;
+  }
+
+  // ---- phase 3: apply the 32 reflectors to my rows ----
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    const double scale = sctab[c], beta = betab[c];
+#pragma unroll
+    for (int i = 0; i < NRL; ++i) {
+      const int grow = row_lo + i * PQ_NT + tid;
+      if (grow >= c) {
+        const double vr = grow > c ? scale * pr[i][c] : 1.0;
+#pragma unroll
+        for (int k = c + 1; k < CB; ++k) pr[i][k] = fma(-vr, wtab[c * CB + k], pr[i][k]);
+        pr[i][c] = grow > c ? vr : beta;
+      }
+    }
+  }
+
+  // ---- phase 4: T from the Gram matrix of the reflectors (dlarft) ----
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NRL; ++i) {
+    const int grow = row_lo + i * PQ_NT + tid;
+#pragma unroll
+    for (int k = 0; k < CB; ++k) Ys[(size_t)k * LDR + i * PQ_NT + tid] = grow > k ? pr[i][k] : (grow == k ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  gram_local();
+  gram_reduce();
+  if (rank == 0 && wid == 0) {
+    double trow[CB];                              // lane i owns row i of T
+#pragma unroll
+    for (int c = 0; c < CB; ++c) trow[c] = 0.0;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const double tau = tautab[c];
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < c; ++k) {
+        const double zz = Gs[k * PG_LDS + c];
+        if ((k & 3) == 0) acc0 = fma(trow[k], zz, acc0);
+        else if ((k & 3) == 1) acc1 = fma(trow[k], zz, acc1);
+        else if ((k & 3) == 2) acc2 = fma(trow[k], zz, acc2);
+        else acc3 = fma(trow[k], zz, acc3);
+      }
+      trow[c] = lane < c ? -tau * ((acc0 + acc1) + (acc2 + acc3)) : (lane == c ? tau : 0.0);
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) a.T[lane + c * CB] = trow[c];
+    a.tau[a.j + lane] = tautab[lane];
+  }
+  // ---- outputs ----
+#pragma unroll
+  for (int i = 0; i < NRL; ++i) {
+    const int r = i * PQ_NT + tid;
+    if (r < nr) {
+      const int grow = row_lo + r;
+#pragma unroll
+      for (int k = 0; k < CB; ++k) {
+        const double v = pr[i][k];
+        a.Y[(r0 + grow) + (long long)(a.j + k) * a.ldy] = grow > k ? v : (grow == k ? 1.0 : 0.0);
+        a.A[(r0 + grow) + (long long)(a.j + k) * a.lda] = grow <= k ? v : 0.0;
+      }
+    }
+  }
+  cluster.sync();
+}
+
+// NRL > 0: rp = 256 NRL and the panel lives in REGISTERS (row i*256 + tid of the CTA's slice in pr[i][0..31]);
+// NRL == 0: any rp (multiple of 256), the panel lives in shared memory.
+template <int NRL>
 __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool prof = a.prof != nullptr;
@@ -551,33 +914,48 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
     pc[slot] += _n - tk;              \
     tk = _n;                          \
   }
+  constexpr bool REG = NRL > 0;
+  constexpr int NR = REG ? NRL : 1;
+  if (a.only_if && *a.only_if == 0) return;       // uniform over the whole cluster
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
   extern __shared__ double sm[];
   const int rp = a.rp, ldp = a.ldp;
-  double* P = sm;                              // 32 columns x rp rows, column-major (ld = ldp, odd)
-  double* ex = P + (size_t)CB * ldp;           // [2][PQ_MAXCS][32] partial dots
-  double* piv = ex + 2 * PQ_MAXCS * CB;        // [2][32] pivot row
+  double* ex = sm;                             // [2][PQ_MAXCS][32] partial dots
+  double* piv = ex + 2 * PQ_MAXCS * CB;        // [2][32] pivot row (as exchanged)
   double* wpart = piv + 2 * CB;                // [2][PQ_NW][32] per-warp partial dots
   double* wsw = wpart + 2 * PQ_NW * CB;        // [PQ_NW][32] update coefficients, one copy per warp
   double* Zm = wsw + PQ_NW * CB;               // [32*32] Zm[k + c*32] = y_k' y_c (k < c)
   double* sT = Zm + CB * CB;                   // [32*32] T factor
   double* stau = sT + CB * CB;                 // [32]
+  double* pivs = stau + CB;                    // [32] pivot row staged by its owner thread (register path)
+  double* P = pivs + CB;                       // shared-memory path: 32 columns x rp rows, column-major (ld = ldp, odd)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int r0 = a.j + CB, m = a.n - r0;
   const int kb = min(CB, m - 1);
   const int row_lo = rank * rp;
   const int nr = max(0, min(m, row_lo + rp) - row_lo);
   const int nrl = rp / PQ_NT;                  // rows per lane
-  for (int rb = tid; rb < rp; rb += PQ_NT) {
-    const double* src = a.A + (r0 + row_lo + rb) + (long long)a.j * a.lda;
+  double pr[NR][CB];
+  if (REG) {
 #pragma unroll
-    for (int k0 = 0; k0 < CB; k0 += 8) {           // eight loads in flight per thread
-      double tmp[8];
+    for (int i = 0; i < NR; ++i) {
+      const int r = i * PQ_NT + tid;
+      const double* src = a.A + (r0 + row_lo + r) + (long long)a.j * a.lda;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) tmp[u] = rb < nr ? src[(long long)(k0 + u) * a.lda] : 0.0;
+      for (int k = 0; k < CB; ++k) pr[i][k] = r < nr ? src[(long long)k * a.lda] : 0.0;
+    }
+  } else {
+    for (int rb = tid; rb < rp; rb += PQ_NT) {
+      const double* src = a.A + (r0 + row_lo + rb) + (long long)a.j * a.lda;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) P[(size_t)(k0 + u) * ldp + rb] = tmp[u];
+      for (int k0 = 0; k0 < CB; k0 += 8) {           // eight loads in flight per thread
+        double tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tmp[u] = rb < nr ? src[(long long)(k0 + u) * a.lda] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) P[(size_t)(k0 + u) * ldp + rb] = tmp[u];
+      }
     }
   }
   for (int idx = tid; idx < CB * CB; idx += PQ_NT) {
@@ -590,17 +968,35 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
   PQ_TICK(0)
   for (int c = 0; c < kb; ++c) {
     const int par = c & 1;
+    const int prank = c / rp, rc = c - prank * rp;     // owner CTA and local row of the pivot row
     // (A) products of my rows (strictly below the pivot row) with every column, reduced over the warp
     {
       double val[CB];
 #pragma unroll
       for (int k = 0; k < CB; ++k) val[k] = 0.0;
-      for (int i = 0; i < nrl; ++i) {
-        const int r = i * PQ_NT + tid;
-        if (row_lo + r > c && r < nr) {
-          const double pc = P[(size_t)c * ldp + r];
+      if (REG) {
 #pragma unroll
-          for (int k = 0; k < CB; ++k) val[k] = fma(pc, P[(size_t)k * ldp + r], val[k]);
+        for (int i = 0; i < NR; ++i) {
+          const int r = i * PQ_NT + tid;
+          double pcv = 0.0;
+#pragma unroll
+          for (int k = 0; k < CB; ++k) pcv = k == c ? pr[i][k] : pcv;
+          if (!(row_lo + r > c && r < nr)) pcv = 0.0;
+#pragma unroll
+          for (int k = 0; k < CB; ++k) val[k] = fma(pcv, pr[i][k], val[k]);
+          if (rank == prank && r == rc) {
+#pragma unroll
+            for (int k = 0; k < CB; ++k) pivs[k] = pr[i][k];
+          }
+        }
+      } else {
+        for (int i = 0; i < nrl; ++i) {
+          const int r = i * PQ_NT + tid;
+          if (row_lo + r > c && r < nr) {
+            const double pcv = P[(size_t)c * ldp + r];
+#pragma unroll
+            for (int k = 0; k < CB; ++k) val[k] = fma(pcv, P[(size_t)k * ldp + r], val[k]);
+          }
         }
       }
 #pragma unroll
@@ -618,14 +1014,15 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
     PQ_TICK(1)
     __syncthreads();
     PQ_TICK(2)
-    // (B) CTA partial -> exchange buffers of every CTA; the owner of the pivot row adds that row
-    if (wid == 0) {
+    // (B) CTA partial -> exchange buffers of every CTA (warp w serves the destinations w, w + 8); the owner of the
+    //     pivot row adds that row
+    {
       double tot = 0.0;
 #pragma unroll
       for (int w = 0; w < PQ_NW; ++w) tot += wpart[((size_t)par * PQ_NW + w) * CB + lane];
-      const int prank = c / rp;
-      const double pv = rank == prank ? P[(size_t)lane * ldp + (c - row_lo)] : 0.0;
-      for (int dsti = 0; dsti < CS; ++dsti) {
+      double pv = 0.0;
+      if (rank == prank) pv = REG ? pivs[lane] : P[(size_t)lane * ldp + rc];
+      for (int dsti = wid; dsti < CS; dsti += PQ_NW) {
         cluster.map_shared_rank(ex, dsti)[((size_t)par * PQ_MAXCS + rank) * CB + lane] = tot;
         if (rank == prank) cluster.map_shared_rank(piv, dsti)[par * CB + lane] = pv;
       }
@@ -650,8 +1047,8 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
         const double nrm = s2 * rn, aa = fabs(alpha);
         beta = alpha >= 0.0 ? -nrm : nrm;
         tau = fma(aa, rn, 1.0);
-        const double rc = 1.0 / (aa + nrm);
-        scale = alpha >= 0.0 ? rc : -rc;
+        const double rcp = 1.0 / (aa + nrm);
+        scale = alpha >= 0.0 ? rcp : -rcp;
       }
       const double z = pk + scale * g;            // y_k' y_c for k < c;  v_c' P[:, k] for k > c
       wsw[wid * CB + lane] = lane > c ? tau * z : 0.0;
@@ -662,23 +1059,41 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
       __syncwarp();
     }
     PQ_TICK(5)
-    // (D) apply to my rows
+    // (D) apply to my rows (the coefficients of the columns <= c are zero)
     {
       const double* w = wsw + wid * CB;
-      for (int i = 0; i < nrl; ++i) {
-        const int r = i * PQ_NT + tid;
-        if (r >= nr) continue;
-        const int grow = row_lo + r;
-        if (grow >= c) {                           // w[k] = 0 for k <= c: the loop is unrolled with static addresses
-          const double vr = grow > c ? scale * P[(size_t)c * ldp + r] : 1.0;
-          double pk[CB];
+      if (REG) {
+        double wk[CB];
 #pragma unroll
-          for (int k = 0; k < CB; ++k) pk[k] = P[(size_t)k * ldp + r];
+        for (int k = 0; k < CB; ++k) wk[k] = w[k];
 #pragma unroll
-          for (int k = 0; k < CB; ++k) pk[k] = fma(-vr, w[k], pk[k]);
+        for (int i = 0; i < NR; ++i) {
+          const int grow = row_lo + i * PQ_NT + tid;
+          if (grow >= c) {
+            double pcv = 0.0;
 #pragma unroll
-          for (int k = 0; k < CB; ++k) P[(size_t)k * ldp + r] = pk[k];
-          P[(size_t)c * ldp + r] = grow > c ? vr : beta;
+            for (int k = 0; k < CB; ++k) pcv = k == c ? pr[i][k] : pcv;
+            const double vr = grow > c ? scale * pcv : 1.0;
+#pragma unroll
+            for (int k = 0; k < CB; ++k) pr[i][k] = k == c ? (grow > c ? vr : beta) : fma(-vr, wk[k], pr[i][k]);
+          }
+        }
+      } else {
+        for (int i = 0; i < nrl; ++i) {
+          const int r = i * PQ_NT + tid;
+          if (r >= nr) continue;
+          const int grow = row_lo + r;
+          if (grow >= c) {
+            const double vr = grow > c ? scale * P[(size_t)c * ldp + r] : 1.0;
+            for (int k0 = (c + 1) & ~7; k0 < CB; k0 += 8) {     // columns <= c inside the first chunk have w = 0
+              double pk8[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) pk8[u] = P[(size_t)(k0 + u) * ldp + r];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) P[(size_t)(k0 + u) * ldp + r] = fma(-vr, w[k0 + u], pk8[u]);
+            }
+            P[(size_t)c * ldp + r] = grow > c ? vr : beta;
+          }
         }
       }
       __syncwarp();
@@ -695,26 +1110,47 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
       const double tau = stau[c];
-      double acc = 0.0;
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
-      for (int k = 0; k < c; ++k) acc = fma(trow[k], Zm[k + c * CB], acc);   // trow[k] = 0 for k < lane
-      trow[c] = lane < c ? -tau * acc : (lane == c ? tau : 0.0);
+      for (int k = 0; k < c; ++k) {                 // trow[k] = 0 for k < lane
+        const double zz = Zm[k + c * CB];
+        if ((k & 3) == 0) acc0 = fma(trow[k], zz, acc0);
+        else if ((k & 3) == 1) acc1 = fma(trow[k], zz, acc1);
+        else if ((k & 3) == 2) acc2 = fma(trow[k], zz, acc2);
+        else acc3 = fma(trow[k], zz, acc3);
+      }
+      trow[c] = lane < c ? -tau * ((acc0 + acc1) + (acc2 + acc3)) : (lane == c ? tau : 0.0);
     }
 #pragma unroll
     for (int c = 0; c < CB; ++c) sT[lane + c * CB] = trow[c];
   }
   __syncthreads();
   // outputs: R into the band part of A, Y (unit lower trapezoidal, explicit zeros) into the reflector store
-  for (int k = 0; k < CB; ++k)
-    for (int r = tid; r < nr; r += PQ_NT) {
-      const int grow = row_lo + r;
-      const double v = P[(size_t)k * ldp + r];
-      double y;
-      if (k >= kb) y = 0.0;
-      else y = grow > k ? v : (grow == k ? 1.0 : 0.0);
-      a.Y[(r0 + grow) + (long long)(a.j + k) * a.ldy] = y;
-      a.A[(r0 + grow) + (long long)(a.j + k) * a.lda] = (k >= kb || grow <= k) ? v : 0.0;
+  if (REG) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = i * PQ_NT + tid;
+      if (r < nr) {
+        const int grow = row_lo + r;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+          const double v = pr[i][k];
+          const double y = k >= kb ? 0.0 : (grow > k ? v : (grow == k ? 1.0 : 0.0));
+          a.Y[(r0 + grow) + (long long)(a.j + k) * a.ldy] = y;
+          a.A[(r0 + grow) + (long long)(a.j + k) * a.lda] = (k >= kb || grow <= k) ? v : 0.0;
+        }
+      }
     }
+  } else {
+    for (int k = 0; k < CB; ++k)
+      for (int r = tid; r < nr; r += PQ_NT) {
+        const int grow = row_lo + r;
+        const double v = P[(size_t)k * ldp + r];
+        const double y = k >= kb ? 0.0 : (grow > k ? v : (grow == k ? 1.0 : 0.0));
+        a.Y[(r0 + grow) + (long long)(a.j + k) * a.ldy] = y;
+        a.A[(r0 + grow) + (long long)(a.j + k) * a.lda] = (k >= kb || grow <= k) ? v : 0.0;
+      }
+  }
   if (rank == 0) {
     for (int idx = tid; idx < CB * CB; idx += PQ_NT) a.T[idx] = sT[idx];
     if (tid < CB) a.tau[a.j + tid] = stau[tid];
@@ -725,67 +1161,178 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
     for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + i, (unsigned long long)pc[i]);
 }
 
-// Z0 = A22 Y (A22 symmetric m x m, full storage; Y m x 32): CTA (rb, ks) accumulates the 64 x 32 tile of rows
-// 64 rb .. over the k range of split ks and writes it to Zpart[ks]; it also forms its share of G0 = Y' Z0 = Y' A22 Y.
+// Z0 = A22 Y (A22 symmetric m x m, full storage, leading dimension even; Y m x 32) on the FP64 tensor cores (DMMA
+// m8n8k4): CTA (rb, ks) accumulates the 64 x 32 tile of rows 64 rb .. over the k range of split ks (chunks of 64 through a
+// two-stage cp.async ring) and writes it to Zpart[ks]; it also forms its share of G0 = Y' Z0 = Y' A22 Y.
 // k_reduce_g sums the shares in a fixed order (deterministic).
-constexpr int SY_BM = 64, SY_BK = 32;
-__global__ void __launch_bounds__(256) k_symm_y(const double* __restrict__ A, long long lda, const double* __restrict__ Y, long long ldy, int m,
-                                                int ksplit, double* __restrict__ Zpart, long long ldz, double* __restrict__ Gpart) {
-  __shared__ double raw[SY_BK * (SY_BM + 1) + SY_BK * (CB + 1)];
-  __shared__ double Yr[SY_BM][CB + 1];
-  double (*As)[SY_BM + 1] = reinterpret_cast<double (*)[SY_BM + 1]>(raw);                       // As[kk][row]
-  double (*Ys)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(raw + SY_BK * (SY_BM + 1));       // Ys[kk][col]
-  double (*Zs)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(raw);                             // after the k loop: 64 x 33
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+constexpr int SY_BM = 64, SY_BK = 64, SY_LD = SY_BK + 4;
+constexpr int SY_STAGE = SY_BK * (SY_BM + 4) + CB * SY_LD;     // doubles per stage: A tile [k][m] (ld 68) + Y tile [n][k] (ld 68)
+__global__ void __launch_bounds__(128) k_symm_y(const double* __restrict__ A, long long lda, const double* __restrict__ Y, long long ldy, int m,
+                                                int ksplit, double* __restrict__ Zpart, long long ldz, double* __restrict__ Gpart, int vec) {
+  extern __shared__ double smy[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int rb = blockIdx.x, ks = blockIdx.y;
   const int row0 = rb * SY_BM;
   const int kchunk = ((m + ksplit - 1) / ksplit + SY_BK - 1) / SY_BK * SY_BK;
   const int k0 = ks * kchunk, k1 = min(m, k0 + kchunk);
-  double acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-  for (int kk0 = k0; kk0 < k1; kk0 += SY_BK) {
-    // A tile: rows row0 .. +63, columns kk0 .. +31 (column-major source: rows contiguous)
-    for (int idx = tid; idx < SY_BK * SY_BM; idx += 256) {
-      const int r = idx & (SY_BM - 1), kk = idx >> 6;
+  const int nit = k1 > k0 ? (k1 - k0 + SY_BK - 1) / SY_BK : 0;
+  auto load_stage = [&](int it, int st) {
+    double* As = smy + st * SY_STAGE;                 // As[kk * 68 + r]
+    double* Ys = As + SY_BK * (SY_BM + 4);            // Ys[n * 68 + kk]
+    const int kk0 = k0 + it * SY_BK;
+    for (int idx = tid; idx < SY_BK * (SY_BM / 2); idx += 128) {      // 16-byte chunks: 32 per k column
+      const int kk = idx >> 5, r = (idx & 31) * 2;
       const int gr = row0 + r, gk = kk0 + kk;
-      As[kk][r] = (gr < m && gk < k1) ? A[gr + (long long)gk * lda] : 0.0;
+      double* dst = As + kk * (SY_BM + 4) + r;
+      const double* src = A + gr + (long long)gk * lda;
+      if (vec) {                                   // m, lda even: rows come in aligned pairs
+        cpa16(dst, src, gr < m && gk < k1);
+      } else {
+        cpa8(dst, src, gr < m && gk < k1);
+        cpa8(dst + 1, src + 1, gr + 1 < m && gk < k1);
+      }
     }
-    for (int idx = tid; idx < SY_BK * CB; idx += 256) {
-      const int kk = idx & 31, col = idx >> 5;
+    for (int idx = tid; idx < CB * (SY_BK / 2); idx += 128) {
+      const int nn = idx >> 5, kk = (idx & 31) * 2;
       const int gk = kk0 + kk;
-      Ys[kk][col] = gk < k1 ? Y[gk + (long long)col * ldy] : 0.0;
+      double* dst = Ys + nn * SY_LD + kk;
+      const double* src = Y + gk + (long long)nn * ldy;
+      if (vec) {
+        cpa16(dst, src, gk < k1);
+      } else {
+        cpa8(dst, src, gk < k1);
+        cpa8(dst + 1, src + 1, gk + 1 < k1);
+      }
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < SY_BK; ++kk) {
-      const double yv = Ys[kk][tx];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double acc[2][4][2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fma(As[kk][ty * 8 + i], yv, acc[i]);
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  if (nit > 0) load_stage(0, 0);
+  for (int it = 0; it < nit; ++it) {
+    if (it + 1 < nit) load_stage(it + 1, (it + 1) & 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const double* As = smy + (it & 1) * SY_STAGE;
+    const double* Ys = As + SY_BK * (SY_BM + 4);
+    const int kk0 = k0 + it * SY_BK;
+    const int klim = min(SY_BK, k1 - kk0);            // rows of Y beyond k1 were zero-filled; columns of A beyond k1 too
+    (void)klim;
+#pragma unroll 4
+    for (int kq = 0; kq < SY_BK / 4; ++kq) {
+      const int k = kq * 4 + t;
+      double af[2], bf[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) af[i] = As[k * (SY_BM + 4) + warp * 16 + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Ys[(j * 8 + g) * SY_LD + k];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncthreads();
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // this thread holds Z[row = warp*16 + 8i + g][col = 8j + 2t + e]
+  double (*Zs)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(smy);                       // 64 x 33
+  double (*Yr)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(smy + SY_BM * (CB + 1));    // 64 x 33
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int gr = row0 + ty * 8 + i;
-    Zs[ty * 8 + i][tx] = acc[i];
-    if (gr < m) Zpart[(long long)ks * ldz * CB + gr + (long long)tx * ldz] = acc[i];
-  }
-  for (int idx = tid; idx < SY_BM * CB; idx += 256) {
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = warp * 16 + i * 8 + g, col = j * 8 + 2 * t + e;
+        Zs[r][col] = acc[i][j][e];
+      }
+  for (int idx = tid; idx < SY_BM * CB; idx += 128) {
     const int r = idx & (SY_BM - 1), col = idx >> 6;
     Yr[r][col] = (row0 + r < m) ? Y[(row0 + r) + (long long)col * ldy] : 0.0;
   }
   __syncthreads();
-  // G share: Gp[i][j] = sum_r Yr[r][i] Zs[r][j]; thread computes i = ty*4 .. +3, j = tx
+  for (int idx = tid; idx < SY_BM * CB; idx += 128) {       // coalesced store of the tile
+    const int r = idx & (SY_BM - 1), col = idx >> 6;
+    if (row0 + r < m) Zpart[(long long)ks * ldz * CB + (row0 + r) + (long long)col * ldz] = Zs[r][col];
+  }
+  // G share: Gp[i][j] = sum_r Yr[r][i] Zs[r][j]; thread computes i = warp*8 .. +7, j = lane
   double* gp = Gpart + ((long long)ks * gridDim.x + rb) * (CB * CB);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int i = ty * 4 + q;
-    double g = 0.0;
+  for (int q = 0; q < 8; ++q) {
+    const int i = warp * 8 + q;
+    double g0 = 0.0, g1 = 0.0;
 #pragma unroll 8
-    for (int r = 0; r < SY_BM; ++r) g = fma(Yr[r][i], Zs[r][tx], g);
-    gp[i + tx * CB] = g;
+    for (int r = 0; r < SY_BM; r += 2) {
+      g0 = fma(Yr[r][i], Zs[r][lane], g0);
+      g1 = fma(Yr[r + 1][i], Zs[r + 1][lane], g1);
+    }
+    gp[i + lane * CB] = g0 + g1;
   }
+}
+
+// C (m x m, column-major, ldc) -= L R' with L, R m x 64 (leading dimension ldp): the rank-64 two-sided update
+// A22 -= [Y W][W Y]' of the band reduction, one 64 x 64 tile per CTA, both operand tiles resident in shared memory.
+constexpr int RU_LD = 64 + 4;
+__global__ void __launch_bounds__(128) k_rank64_update(double* __restrict__ C, long long ldc, const double* __restrict__ L,
+                                                       const double* __restrict__ R, long long ldp, int m) {
+  extern __shared__ double smu[];
+  double* Ls = smu;                    // Ls[k * 68 + r]
+  double* Rs = smu + 64 * RU_LD;       // Rs[k * 68 + c]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  for (int idx = tid; idx < 64 * 32; idx += 128) {
+    const int kk = idx >> 5, r = (idx & 31) * 2;
+    cpa16(Ls + kk * RU_LD + r, L + (m0 + r) + (long long)kk * ldp, m0 + r < m);
+    cpa16(Rs + kk * RU_LD + r, R + (n0 + r) + (long long)kk * ldp, n0 + r < m);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  // prefetch the C tile entries this thread updates while the operands arrive
+  double cv[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = m0 + wm + i * 8 + g, cidx = n0 + wn + j * 8 + 2 * t + e;
+        cv[i][j][e] = (r < m && cidx < m) ? C[r + (long long)cidx * ldc] : 0.0;
+      }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+  for (int kq = 0; kq < 16; ++kq) {
+    const int k = kq * 4 + t;
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) af[i] = Ls[k * RU_LD + wm + i * 8 + g];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = Rs[k * RU_LD + wn + j * 8 + g];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = m0 + wm + i * 8 + g, cidx = n0 + wn + j * 8 + 2 * t + e;
+        if (r < m && cidx < m) C[r + (long long)cidx * ldc] = cv[i][j][e] - acc[i][j][e];
+      }
 }
 
 // G0[idx] = sum over the shares (fixed order: 8 interleaved partial sums per entry, combined by a shuffle tree)
@@ -884,11 +1431,11 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   TNAD_REQUIRE(n >= 3 && ldab >= CB + 1, "sb2st: need n >= 3 and a band store with 33 rows");
   TNAD_REQUIRE(c->coop_launch, "sb2st: the chase kernel needs cooperative (co-resident) launches");
   const int NP = (int)chase_positions(n);
-  int W = opt_i(c, "TNAD_CHASE_W", 4);
+  int W = std::max(1, std::min(4, opt_i(c, "TNAD_CHASE_W", 4)));
   while ((NP + W - 1) / W > c->num_sms) ++W;      // all CTAs must be co-resident (one per SM)
-  TNAD_REQUIRE(W <= 8, "sb2st: matrix too large for the chase kernel (n <= 32 * 8 * #SMs)");
+  TNAD_REQUIRE(W <= 4, "sb2st: matrix too large for the chase kernel (n <= 32 * 4 * #SMs)");   // 2 W warps per CTA, 256 threads
   const int G = (NP + W - 1) / W;
-  Tens gbox = t_alloc(c, {(int64_t)NP * 2 * MB_WORDS}, true);
+  Tens gbox = t_alloc(c, {(int64_t)NP * 3 * MB_WORDS}, true);
   Tens err = t_alloc(c, {2}, true);
   ChaseArgs a;
   a.AB = AB; a.ldab = (int)ldab; a.n = (int)n; a.NP = NP; a.W = W;
@@ -896,7 +1443,7 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   a.gbox = reinterpret_cast<unsigned long long*>(gbox.p);
   a.err = reinterpret_cast<int*>(err.p);
   const bool prof = opt_i(c, "TNAD_DC_DEBUG", 0) >= 2;
-  Tens pbuf = t_alloc(c, {(int64_t)NP * 6 + 2}, true);
+  Tens pbuf = t_alloc(c, {(int64_t)NP * 12 + 2}, true);
   a.prof = prof ? reinterpret_cast<long long*>(pbuf.p) : nullptr;
   const size_t smem = (size_t)W * POS_DOUBLES * sizeof(double);
   TNAD_CUDA(cudaFuncSetAttribute(k_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -909,7 +1456,7 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   TNAD_REQUIRE(Gp <= c->num_sms, "sb2st: matrix too large for the chase kernel");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(Gp);
-  cfg.blockDim = dim3(32 * W);
+  cfg.blockDim = dim3(64 * W);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
   cudaLaunchAttribute at[2];
@@ -937,14 +1484,15 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   sync(c);
   if (herr) fail(TNAD_ERR_INTERNAL, "sb2st: the chase pipeline timed out");
   if (prof) {
-    std::vector<long long> ph((size_t)NP * 6);
+    std::vector<long long> ph((size_t)NP * 12);
     TNAD_CUDA(cudaMemcpy(ph.data(), pbuf.p, ph.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    for (int t : {0, 1, 2, 3, 4, 5, NP / 2, NP / 2 + 1}) {
+    for (int t : {0, 1, NP / 2, NP / 2 + 1}) {
       if (t >= NP) continue;
       const double ns = (double)std::max<int64_t>(1, std::min<int64_t>(n - 2, n - 1 - CB * t));
-      fprintf(stderr, "[tnad dc] chase position %d (W=%d) cycles/hop: wait row %.0f  wait v %.0f  E phase %.0f  D phase %.0f  sends %.0f  | total/hop %.0f\n",
-              t, W, ph[(size_t)t * 6 + 0] / ns, ph[(size_t)t * 6 + 1] / ns, ph[(size_t)t * 6 + 2] / ns, ph[(size_t)t * 6 + 3] / ns,
-              ph[(size_t)t * 6 + 4] / ns, ph[(size_t)t * 6 + 5] / ns);
+      const long long* e = ph.data() + (size_t)t * 12;
+      const long long* d = e + 6;
+      fprintf(stderr, "[tnad dc] chase position %d (W=%d) cycles/hop  E warp: wait D+row %.0f  wait v %.0f  compute %.0f  row send %.0f  bulk %.0f | %.0f   D warp: load+row %.0f  wait v %.0f  first half %.0f  bulk %.0f | %.0f\n",
+              t, W, e[0] / ns, e[1] / ns, e[2] / ns, e[4] / ns, e[3] / ns, e[5] / ns, d[0] / ns, d[1] / ns, d[3] / ns, d[4] / ns, d[5] / ns);
     }
   }
 }
@@ -977,13 +1525,6 @@ void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, in
   }
 }
 
-static Tens bview(double* p, int64_t rows, int64_t cols, int64_t ld) {
-  Tens t = t_wrap(p, {rows, cols});
-  t.str[0] = 1;
-  t.str[1] = ld;
-  return t;
-}
-
 // Dense symmetric A (n x n, full storage, overwritten) -> band: on return the band (|i - j| <= 32) of the lower
 // triangle of A holds B; Yst (n x n, ldy, zero-initialised) receives the reflectors of panel j in columns j .. j+31
 // (rows >= j + 32, unit element of column c at row c + 32), tau1 (n, zero-initialised) their scalars.
@@ -994,14 +1535,31 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
   const int64_t nrb_max = (n + SY_BM - 1) / SY_BM;
   Tens Tb = t_alloc(c, {CB, CB}), Mb = t_alloc(c, {CB, CB}), Zp = t_alloc(c, {n, CB, (int64_t)ksplit_max});
   Tens Gp = t_alloc(c, {CB * CB, nrb_max * ksplit_max});
-  Tens P1 = t_alloc(c, {n, 2 * CB}), P2 = t_alloc(c, {n, 2 * CB});
+  const int64_t ldpp = (n + 1) & ~1LL;       // even leading dimensions: the tile loaders move 16-byte chunks
+  Tens P1 = t_alloc(c, {ldpp, 2 * CB}), P2 = t_alloc(c, {ldpp, 2 * CB});
   static std::atomic<unsigned long long> attr_devs{0};
   if (!((attr_devs.load(std::memory_order_acquire) >> (c->device & 63)) & 1ULL)) {
-    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_qr<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_gram<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    TNAD_CUDA(cudaFuncSetAttribute(k_panel_gram<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    TNAD_CUDA(cudaFuncSetAttribute(k_symm_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SY_STAGE * sizeof(double))));
+    TNAD_CUDA(cudaFuncSetAttribute(k_rank64_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * RU_LD * sizeof(double))));
     attr_devs.fetch_or(1ULL << (c->device & 63), std::memory_order_release);
   }
-  const size_t fixed = (size_t)(2 * PQ_MAXCS * CB + 2 * CB + 2 * PQ_NW * CB + PQ_NW * CB + 2 * CB * CB + CB) * sizeof(double);
+  const size_t fixed = (size_t)(2 * PQ_MAXCS * CB + 2 * CB + 2 * PQ_NW * CB + PQ_NW * CB + 2 * CB * CB + 2 * CB) * sizeof(double);
+  const bool use_regs = opt_i(c, "TNAD_PANEL_REGS", 1) != 0;
+  const bool use_gram = opt_i(c, "TNAD_PANEL_GRAM", 1) != 0;
+  auto gram_smem = [](int nrl) {
+    return (size_t)(CB * (PQ_NT * nrl + 4) + 4 * CB * PG_LDS + 3 * CB * CB + 3 * CB + 8) * sizeof(double);
+  };
+  Tens fbflag = t_alloc(c, {(n / CB + 2) / 2 + 2}, true);
   const int rp_max = (int)((((232448 - 1024) - fixed) / (CB * sizeof(double)) - 1) / PQ_NT * PQ_NT);
   const bool prof = opt_i(c, "TNAD_DC_DEBUG", 0) >= 2;
   double tph[4] = {0, 0, 0, 0};
@@ -1009,11 +1567,12 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
   cudaEvent_t pe[5];
   if (prof)
     for (auto& e : pe) e = get_event(c);
+  const auto host_t0 = std::chrono::steady_clock::now();
   for (int64_t j = 0; j + CB < n - 1; j += CB) {
     const int64_t r0 = j + CB, m = n - r0;
     int CS = (int)std::min<int64_t>(8, std::max<int64_t>(1, (m + PQ_NT - 1) / PQ_NT));
     int rp = (int)(((m + CS - 1) / CS + PQ_NT - 1) / PQ_NT * PQ_NT);
-    if (rp > rp_max) {
+    if (rp > 2 * PQ_NT) {   // more than two rows per lane: a cluster of 16 keeps the panel in registers up to m = 8192
       CS = PQ_MAXCS;
       rp = (int)(((m + CS - 1) / CS + PQ_NT - 1) / PQ_NT * PQ_NT);
     }
@@ -1022,22 +1581,58 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     pa.A = A; pa.lda = lda; pa.n = (int)n; pa.j = (int)j; pa.rp = rp; pa.ldp = rp + 1;
     pa.Y = Yst; pa.ldy = ldy; pa.tau = tau1; pa.T = Tb.p;
     pa.prof = prof ? reinterpret_cast<long long*>(pprof.p) : nullptr;
+    pa.only_if = nullptr;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    if (prof) TNAD_CUDA(cudaEventRecord(pe[0], st));
+    // fast path: Gram-driven factorisation (no exchange per column); it raises fbflag[panel] when a column cancels
+    int* fbp = reinterpret_cast<int*>(fbflag.p) + (j / CB);
+    bool gram = use_gram && m >= CB + 1;
+    if (gram) {
+      int gnrl = 1, gcs = 1;
+      while (gcs * PQ_NT < m && gcs < PQ_MAXCS) gcs *= 2;
+      if ((int64_t)gcs * PQ_NT < m) {
+        gnrl = 2;
+        gcs = 1;
+        while (gcs * 2 * PQ_NT < m && gcs < PQ_MAXCS) gcs *= 2;
+      }
+      if ((int64_t)gcs * gnrl * PQ_NT < m) gram = false;
+      if (gram) {
+        PanelArgs pg = pa;
+        pg.rp = gnrl * PQ_NT;
+        pg.prof = nullptr;
+        cudaLaunchConfig_t cg_ = {};
+        cg_.gridDim = dim3(gcs);
+        cg_.blockDim = dim3(PQ_NT);
+        cg_.dynamicSmemBytes = gram_smem(gnrl);
+        cg_.stream = st;
+        at[0].val.clusterDim.x = gcs;
+        cg_.attrs = at;
+        cg_.numAttrs = 1;
+        KTimer kt(c, KF_EIG);
+        if (gnrl == 1) TNAD_CUDA(cudaLaunchKernelEx(&cg_, k_panel_gram<1>, pg, fbp));
+        else TNAD_CUDA(cudaLaunchKernelEx(&cg_, k_panel_gram<2>, pg, fbp));
+        c->launches++;
+        pa.only_if = fbp;
+      }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS);
     cfg.blockDim = dim3(PQ_NT);
-    cfg.dynamicSmemBytes = fixed + (size_t)CB * (rp + 1) * sizeof(double);
+    const int nrl = rp / PQ_NT;
+    const bool regs = use_regs && nrl <= 2;
+    cfg.dynamicSmemBytes = fixed + (regs ? 0 : (size_t)CB * (rp + 1) * sizeof(double));
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (prof) TNAD_CUDA(cudaEventRecord(pe[0], st));
     {
       KTimer kt(c, KF_EIG);
-      TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr, pa));
+      if (regs && nrl == 1) TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr<1>, pa));
+      else if (regs) TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr<2>, pa));
+      else TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr<0>, pa));
     }
     c->launches++;
     if (prof) TNAD_CUDA(cudaEventRecord(pe[1], st));
@@ -1049,18 +1644,22 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     ksplit = (int)std::min<int64_t>(ksplit, (m + 4 * SY_BK - 1) / (4 * SY_BK));
     {
       KTimer kt(c, KF_GEMM);
-      k_symm_y<<<dim3(nrb, ksplit), 256, 0, st>>>(A22p, lda, Yp, ldy, (int)m, ksplit, Zp.p, n, Gp.p);
+      k_symm_y<<<dim3(nrb, ksplit), 128, 2 * SY_STAGE * sizeof(double), st>>>(A22p, lda, Yp, ldy, (int)m, ksplit, Zp.p, n, Gp.p,
+                                                                                    (n % 2 == 0 && lda % 2 == 0 && ldy % 2 == 0) ? 1 : 0);
       LAUNCH_CHECK(c);
       k_reduce_g<<<CB * CB * 8 / 256, 256, 0, st>>>(Gp.p, nrb * ksplit, Mb.p);
     }
     LAUNCH_CHECK(c);
     if (prof) TNAD_CUDA(cudaEventRecord(pe[2], st));
-    k_make_w<<<(int)((m + 31) / 32), 256, 0, st>>>(Zp.p, n, ksplit, Yp, ldy, Tb.p, Mb.p, (int)m, P1.p, P2.p, n);
+    k_make_w<<<(int)((m + 31) / 32), 256, 0, st>>>(Zp.p, n, ksplit, Yp, ldy, Tb.p, Mb.p, (int)m, P1.p, P2.p, ldpp);
     LAUNCH_CHECK(c);
     if (prof) TNAD_CUDA(cudaEventRecord(pe[3], st));
-    Tens A22 = bview(A22p, m, m, lda);
-    Tens L = bview(P1.p, m, 2 * CB, n), R = bview(P2.p, m, 2 * CB, n);
-    contract(c, "ik,jk->ij", L, R, A22, -1.0, 1.0);
+    {
+      KTimer kt(c, KF_GEMM);
+      const int nt = (int)((m + 63) / 64);
+      k_rank64_update<<<dim3(nt, nt), 128, 2 * 64 * RU_LD * sizeof(double), st>>>(A22p, lda, P1.p, P2.p, ldpp, (int)m);
+    }
+    LAUNCH_CHECK(c);
     if (prof) {
       TNAD_CUDA(cudaEventRecord(pe[4], st));
       TNAD_CUDA(cudaEventSynchronize(pe[4]));
@@ -1071,6 +1670,9 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
       }
     }
   }
+  if (opt_i(c, "TNAD_DC_DEBUG", 0) == 1)
+    fprintf(stderr, "[tnad dc] sy2sb host enqueue time %.2f ms\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
   if (prof) {
     fprintf(stderr, "[tnad dc] sy2sb n=%lld (synchronised per panel): panel QR %.2f  Z0=A22*Y + G0 %.2f  make_w %.2f  update %.2f ms\n",
             (long long)n, tph[0], tph[1], tph[2], tph[3]);
