@@ -140,7 +140,7 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------
 def cpu_reference_sample(sample_maxit):
     """The reference's CPU path (oracle port: NumPy/SciPy -> OpenBLAS dgemm + LAPACK dgesdd, all host threads)
-    on a bounded sample of the workload: same tensor, same chi, `maxit = sample_maxit`."""
+    on the workload's tensor and chi with `maxit = sample_maxit`."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import tnad_oracle as O
     try:    # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core it can use
@@ -153,36 +153,43 @@ def cpu_reference_sample(sample_maxit):
     t0 = time.perf_counter()
     e, g = O.energy_value_and_grad(h, A, CHI, 0.0, sample_maxit, info=info)
     dt = time.perf_counter() - t0
-    return dt, info["nsteps"], float(e)
+    return dt, info["nsteps"], float(e), g
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return int(max([p.get("num_threads", 1) for p in threadpool_info()] + [1]))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU algorithm (oracle port, all host threads) on OUR arm's configuration
+    (same tensor, chi and maxit: `same_config` true unless --ref-maxit overrides it)."""
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    try:
-        from threadpoolctl import threadpool_info
-        nthreads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        nthreads = os.cpu_count() or 1
-    sample_maxit = args.ref_maxit
-    for _ in range(args.warmup if args.warmup < 1 else 1):      # one untimed pass pages in BLAS/LAPACK
-        cpu_reference_sample(0)
+    sample_maxit = args.maxit if args.ref_maxit is None else args.ref_maxit
+    cpu_reference_sample(0)                                      # one untimed pass pages in BLAS / LAPACK
     times, nsteps = [], 0
     for _ in range(args.steps):
-        dt, nsteps, _ = cpu_reference_sample(sample_maxit)
+        dt, nsteps, _, _ = cpu_reference_sample(sample_maxit)
         times.append(dt)
     total = float(np.sum(times))
     val = total / (args.steps * nsteps)
+    nthreads = host_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": False, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Heisenberg iPEPS energy+gradient d={D_IPEPS} (D={D_IPEPS**2}) chi={CHI} FP64, tol=0; bounded sample maxit={sample_maxit} "
-                               f"({nsteps} ctmrgsteps per call) of the maxit={MAXIT} workload", "ipeps_d": D_IPEPS, "chi": CHI,
-                   "maxit": sample_maxit, "parallelism": "host threads (OpenBLAS)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(nthreads), "kind": "port",
-                         "sample": f"oracle port (NumPy/SciPy: OpenBLAS dgemm + LAPACK dgesdd), energy+gradient with maxit={sample_maxit}"},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "same_config": sample_maxit == args.maxit,
+        "config": {"workload": f"Heisenberg iPEPS energy+gradient d={D_IPEPS} (CTMRG D={D_IPEPS**2}) chi={CHI} FP64, tol=0 maxit={sample_maxit} "
+                               f"({nsteps} ctmrgsteps forward + unrolled backward per call); BASELINE configs[3]",
+                   "ipeps_d": D_IPEPS, "chi": CHI, "maxit": sample_maxit, "ctmrgsteps_per_call": nsteps,
+                   "parallelism": "host threads (OpenBLAS)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port",
+                         "sample": f"oracle port (NumPy/SciPy: OpenBLAS dgemm + LAPACK dgesdd), energy+gradient, maxit={sample_maxit}, "
+                                   f"{args.steps} calls of {total / args.steps:.1f} s"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -191,6 +198,44 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+FWD_FLOPS_PER_STEP = None
+
+
+def contraction_flops(chi, D, s=2):
+    """Optimal-order algorithmic flops: forward contractions of one ctmrgstep and of expectationvalue."""
+    n = chi * D
+    step = (2 * chi ** 3 * D + 2 * chi ** 3 * D ** 2 + 2 * chi ** 2 * D ** 4) + (2 * n * n * chi + 2 * n * chi ** 2) + (4 * chi ** 3 * D ** 2 + 2 * chi ** 2 * D ** 4)
+    expv = 4 * chi ** 3 * D + 2 * chi ** 3 * D ** 2 + 2 * chi ** 2 * D ** 4 * s * s + 2 * chi ** 3 * D ** 2 * s * s
+    return float(step), float(expv)
+
+
+def measure_trg_chi64(ctx, T):
+    """Third part of BASELINE's metric: steady-state TRG iterations/s at chi=64 (value + gradient).  The bond
+    dimension of the Ising tensor saturates at 64 in iteration 5; iterations 6.. split full 4096 x 4096 matrices:
+    the steady-state cost per iteration is (t(9 iterations) - t(7 iterations)) / 2."""
+    a = T.model_tensor(T.Ising(), 0.44)
+
+    def run(niter):
+        ctx.timer_start()
+        lnz, g = T.trg_value_and_grad(a, 64, niter, ctx=ctx)
+        return ctx.timer_stop(), lnz, g
+    run(7)                                   # grows the stream-ordered pool (first touch) for these sizes
+    t7, lnz7, g7 = run(7)
+    run(9)
+    t9, lnz9, _ = run(9)
+    per_iter = (t9 - t7) / 2.0
+    out = {"iters_per_s": 1e3 / per_iter if per_iter > 0 else None, "ms_per_iteration": per_iter,
+           "ms_7_iterations": t7, "ms_9_iterations": t9, "lnZ_7": lnz7,
+           "workload": "TRG Ising beta=0.44 chi=64, value + gradient, steady state (two 4096x4096 truncated SVDs + 2 chi^6 contraction per iteration)"}
+    fx = os.path.join(ROOT, "tests", "golden", "large.npz")
+    if os.path.exists(fx):
+        vec = np.load(fx)
+        ref, dref = float(vec["trg64_lnz"]), float(vec["trg64_dbeta"])
+        db = float(np.sum(g7 * T.dmodel_tensor(T.Ising(), 0.44)))
+        out["parity_vs_oracle_fixture"] = {"lnZ_rel_err": abs(lnz7 - ref) / abs(ref), "dlnZ_dbeta_rel_err": abs(db - dref) / abs(dref)}
+    return out
+
+
 def run_ours(args):
     import tnad_b200 as T
     dist = Dist()
@@ -199,7 +244,6 @@ def run_ours(args):
     d, s = D_IPEPS, S_PHYS
     h = heisenberg_h()
     A = ipeps_tensor(rank)                      # every rank an independent replica (its own seed)
-    nsteps_per_call = args.maxit + 1
 
     # -- device-resident arm (`value`): inputs and the gradient output live in HBM
     hp, Ap, gp = ctx.dev_alloc(h.size), ctx.dev_alloc(A.size), ctx.dev_alloc(A.size)
@@ -218,7 +262,6 @@ def run_ours(args):
     ms = ctx.timer_stop()
     launches = ctx.launch_count()
     dist.barrier()
-    sampler.stop_flag = True
     ms = dist.max(ms)
     launches_total = int(dist.sum(float(launches)))
     steps_done = ctx.last_steps
@@ -233,95 +276,128 @@ def run_ours(args):
     for _ in range(args.steps):
         e_h, g_h = ctx.energy(hh, Ah, CHI, 0.0, args.maxit, grad=True)
     ms_e2e = dist.max(ctx.timer_stop())
+    sampler.stop_flag = True
     h2d = int(h.nbytes + A.nbytes)
     d2h = int(8 + A.nbytes)
 
+    extra = {}
+    if world > 1:
+        # the north-star multi-GPU configurations (BASELINE configs[4]): the 64-instance TRG beta sweep (no collective)
+        # and the chi-sharded ctmrgstep at d=5, chi=256 (NCCL all-gather of the enlarged corner)
+        import bench_sweep
+        import bench_sharded
+        try:
+            sw = bench_sweep.measure(dist, ctx, 64, 20, 20)
+            extra["sweep_instances_per_s"] = sw["instances_per_s"]
+            extra["sweep"] = sw
+        except Exception as ex:   # noqa: BLE001
+            extra["sweep_error"] = repr(ex)
+        try:
+            if 256 % world == 0:
+                sh = bench_sharded.measure(dist, ctx, 5, 256, 2, 1, False)
+                extra["sharded_s_per_step"] = sh["s_per_step"]
+                extra["sharded_ms_contract"] = sh["ms_contract"]
+                extra["sharded_ms_gather"] = sh["ms_gather"]
+                extra["sharded_ms_svd"] = sh["ms_svd"]
+                extra["sharded"] = sh
+        except Exception as ex:   # noqa: BLE001
+            extra["sharded_error"] = repr(ex)
+
     if rank == 0:
-        # -- roofline of the dominant kernel family (extra instrumented pass, outside the timed regions)
+        # -- per-kernel-family device time (extra instrumented pass, outside the timed regions)
         ctx.set_kernel_timing(True)
         ctx.energy_device(hp, Ap, d, s, CHI, 0.0, args.maxit, gp)
         kt = ctx.kernel_timing()
         ctx.set_kernel_timing(False)
         dmma_peak = ctx.dmma_peak()
-        gemm_tf = ctx.gemm_bench(4096, 4096, 4096, 3)
-        # executed work is counted on the device (skipped, already-converged pairs do no work), so the flop
-        # numerators below are exact: one k_sym_update_m block = two 64^3 products, one k_jacobi_update slab =
-        # one 128x64x64 product; the pivot kernel is FP64 vector math (dots + plane rotations).
-        mu, qu, pe = kt["m_update"], kt["q_update"], kt["eig_panel"]
-        fl_m = mu.get("blocks", 0) * 2 * 2.0 * 64 ** 3
-        fl_q = qu.get("slabs", 0) * 2.0 * 128 * 64 * 64
-        tf_m = fl_m / (mu["ms"] * 1e-3) / 1e12 if mu["ms"] > 0 else 0.0
-        tf_q = fl_q / (qu["ms"] * 1e-3) / 1e12 if qu["ms"] > 0 else 0.0
         pk, pk_kind = peaks()
-        traffic = None
+        hbm = float(pk.get("hbm_gbs", 0.0)) or None
+        n_mat = CHI * D_IPEPS ** 2
+        n_svd = steps_done
+        fam_ms = {k: v["ms"] for k, v in kt.items()}
+        dom = max(fam_ms, key=lambda k: fam_ms[k])
+        traffic = {}
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("k_sym_update_m_dram_bytes_per_launch")
-        dom = max(("m_update", "eig_panel", "q_update", "gemm"), key=lambda k: kt[k]["ms"])
-        roof_jacobi = {"bound": "tensor",
-                "kernel": "k_sym_update_m (fused two-sided 64x64 block update M <- W'MW of the symmetric block-Jacobi "
-                          "eigensolver, FP64 DMMA m8n8k4)",
-                "achieved": tf_m, "peak": dmma_peak, "unit": "TFLOP/s", "frac": tf_m / dmma_peak if dmma_peak else None,
-                "traffic": traffic,
-                "flops_per_launch": fl_m / mu["launches"] if mu["launches"] else None,
-                "avg_launch_us": 1e3 * mu["ms"] / mu["launches"] if mu["launches"] else None,
-                "peak_source": "FP64 DMMA issue-rate microbenchmark (tnad_dmma_peak) run in this process: MEASURED_PEAKS.json "
-                               f"carries no FP64 figure (its hbm_gbs={pk.get('hbm_gbs')} [{pk_kind}] bounds the elementwise kernels)",
-                "kernel_ms_instrumented_pass": {k: round(v["ms"], 3) for k, v in kt.items()},
-                "kernel_launches": {k: v["launches"] for k, v in kt.items()},
-                "largest_family_by_device_time": dom,
-                "other_kernels": {
-                    "k_jacobi_update (Q <- Q W panel rotation, FP64 DMMA)": {"achieved_tflops": tf_q, "frac": tf_q / dmma_peak if dmma_peak else None},
-                    "k_sym_eig (64x64 pivot eigenproblem, register-resident Jacobi, FP64 vector + shuffles; latency bound, "
-                    "runs on N/64 SMs concurrently with the DMMA updates)": {"ms": round(pe["ms"], 3), "launches": pe["launches"]},
-                    "gemm_dmma_kernel (einsum contractions) on 4096^3": {"achieved_tflops": gemm_tf, "frac": gemm_tf / dmma_peak if dmma_peak else None}}}
-        if mu["launches"] > 0:
-            roof = roof_jacobi
-        else:
-            # Direct eigensolver (default from n >= 256): the dominant kernel is the persistent tridiagonalisation panel
-            # kernel k_sytrd_panel (timed in the `pivot_eig` slot).  Its algorithmic traffic is the trailing matrix read
-            # once per reflector: 8 * sum_j (n-j-1)^2 bytes per decomposition (~ 8 n^3 / 3), DESIGN.md section 4.2.
-            n_mat = CHI * D_IPEPS ** 2
-            # columns [0, j_tail) run in the grid-wide panel kernel (32 per launch), the last t = n - j_tail <= 416 columns
-            # in ONE launch of the cluster kernel, which loads the trailing matrix once into distributed shared memory
-            j_tail = ((n_mat - 416 + 31) // 32) * 32 if n_mat > 416 else 0
-            panels = j_tail // 32 + 1
-            n_svd = pe["launches"] / panels if panels else 0
-            bytes_svd = 8.0 * sum((n_mat - j - 1) ** 2 for j in range(j_tail)) + 8.0 * (n_mat - j_tail) ** 2
-            gbs = bytes_svd * n_svd / (pe["ms"] * 1e-3) / 1e9 if pe["ms"] > 0 else 0.0
-            hbm = float(pk.get("hbm_gbs", 0.0)) or None
-            tr = None
-            if os.path.exists(tpath):
-                with open(tpath) as f:
-                    tr = json.load(f).get("k_sytrd_panel_dram_bytes_per_launch")
-            roof = {"bound": "hbm",
-                    "kernel": "k_sytrd_panel1 (+ k_sytrd_tail_cluster for the last 416 columns): persistent cooperative Householder "
-                              "tridiagonalisation, per column one matrix-vector product over the trailing matrix and one grid-wide exchange; FP64 vector",
-                    "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm if hbm else None, "traffic": tr,
-                    "bytes_per_launch": bytes_svd / panels if panels else None,
-                    "avg_launch_us": 1e3 * pe["ms"] / pe["launches"] if pe["launches"] else None,
+                traffic = json.load(f)
+        # algorithmic work of the eigensolver's kernels per decomposition
+        b = 32
+        fl_symm = 2.0 * b * sum((n_mat - j - b) ** 2 for j in range(0, n_mat - b - 1, b))          # Z0 = A22 Y per panel
+        fl_r64 = 2.0 * 2 * b * sum((n_mat - j - b) ** 2 for j in range(0, n_mat - b - 1, b))       # A22 -= [Y W][W Y]'
+        fl_q2 = 2.0 * n_mat ** 3                                                                  # n^2 / (2 b) reflectors x 4 b n
+        by_chase = 8.0 * (33 * n_mat + n_mat * (n_mat - 2) / 2 + n_mat * (n_mat - 2) / (2 * b))    # band in, reflectors + taus out
+
+        def tf(flops_per_svd, fam):
+            t = kt[fam]["ms"] * 1e-3
+            return flops_per_svd * n_svd / t / 1e12 if t > 0 else None
+        kernels = {
+            "k_chase (band -> tridiagonal, systolic bulge chasing; bound by the chain of 2n dependent hops)": {
+                "ms": round(kt["chase"]["ms"], 3), "launches": kt["chase"]["launches"], "bound": "hbm",
+                "achieved_gbs": by_chase * n_svd / (kt["chase"]["ms"] * 1e-3) / 1e9 if kt["chase"]["ms"] > 0 else None,
+                "algorithmic_bytes_per_launch": by_chase},
+            "k_q2_stage (back-transformation with Q2, FP64 vector FMA, register resident)": {
+                "ms": round(kt["q2_stage"]["ms"], 3), "launches": kt["q2_stage"]["launches"], "bound": "fp64 vector",
+                "achieved_tflops": tf(fl_q2, "q2_stage"), "frac_of_fp64_peak": (tf(fl_q2, "q2_stage") or 0) / dmma_peak if dmma_peak else None},
+            "k_panel_gram / k_panel_qr (panel QR of the band reduction, one thread-block cluster)": {
+                "ms": round(kt["panel_qr"]["ms"], 3), "launches": kt["panel_qr"]["launches"], "bound": "latency (serial column recurrence)"},
+            "k_symm_y (+ k_reduce_g): Z0 = A22 Y, FP64 DMMA": {
+                "ms": round(kt["symm_y"]["ms"], 3), "launches": kt["symm_y"]["launches"], "bound": "tensor",
+                "achieved_tflops": tf(fl_symm, "symm_y"), "frac": (tf(fl_symm, "symm_y") or 0) / dmma_peak if dmma_peak else None},
+            "k_rank64_update: A22 -= [Y W][W Y]', FP64 DMMA": {
+                "ms": round(kt["rank64_update"]["ms"], 3), "launches": kt["rank64_update"]["launches"], "bound": "tensor",
+                "achieved_tflops": tf(fl_r64, "rank64_update"), "frac": (tf(fl_r64, "rank64_update") or 0) / dmma_peak if dmma_peak else None},
+            "gemm_dmma_kernel (einsum contractions, svd_back, back-transformation with Q1, divide-and-conquer merges)": {
+                "ms": round(kt["gemm"]["ms"], 3), "launches": kt["gemm"]["launches"], "bound": "tensor"},
+            "divide and conquer (non-GEMM kernels)": {"ms": round(kt["stedc"]["ms"], 3), "launches": kt["stedc"]["launches"]},
+        }
+        if dom == "chase" or kt["chase"]["ms"] >= max(kt["q2_stage"]["ms"], kt["panel_qr"]["ms"]):
+            ach = by_chase * n_svd / (kt["chase"]["ms"] * 1e-3) / 1e9 if kt["chase"]["ms"] > 0 else 0.0
+            roof = {"bound": "hbm", "kernel": "k_chase: band (half bandwidth 32) -> tridiagonal by bulge chasing, one launch per eigen-decomposition; "
+                                              "systolic array of warps, band resident in shared memory of a thread-block cluster",
+                    "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if hbm else None,
+                    "traffic": traffic.get("k_chase_dram_bytes_per_launch"),
+                    "bytes_per_launch": by_chase, "avg_launch_us": 1e3 * kt["chase"]["ms"] / max(1, kt["chase"]["launches"]),
                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs [{pk_kind}]",
-                    "note": "synchronisation bound at n=2048: the 33.5 MB trailing matrix is L2 resident, every column costs one grid-wide exchange "
-                            "(~3 L2 round trips) plus gather and matvec; the fraction says how far the column loop is from streaming the matrix at HBM speed",
-                    "kernel_ms_instrumented_pass": {("sytrd_panel" if k == "eig_panel" else k): round(v["ms"], 3) for k, v in kt.items()},
-                    "kernel_launches": {("sytrd_panel" if k == "eig_panel" else k): v["launches"] for k, v in kt.items()},
-                    "largest_family_by_device_time": "sytrd_panel" if dom == "eig_panel" else dom,
-                    "other_kernels": {
-                        "gemm_dmma_kernel (einsum contractions, trailing updates, back-transform, D&C merges) on 4096^3":
-                            {"achieved_tflops": gemm_tf, "peak_tflops": dmma_peak, "frac": gemm_tf / dmma_peak if dmma_peak else None}}}
-        # -- CPU baseline on a bounded sample (same box, same run)
-        if args.no_cpu_baseline or world > 1:      # the CPU baseline is measured on rank 0 at N = 1 only
-            cpu = None
+                    "note": "largest single kernel of the call; its HBM traffic (33 n doubles in, n^2/2 reflector doubles out) is negligible: the kernel is "
+                            "bound by the chain of 2n dependent Householder hops (about 2.3 us per sweep), not by any throughput roof. The throughput-bound "
+                            "kernels of the call are listed under `kernels` with their own fractions (FP64 tensor peak from tnad_dmma_peak)"}
         else:
-            cdt, cns, _ = cpu_reference_sample(args.ref_maxit)
+            famname = {"gemm": "gemm_dmma_kernel", "q2_stage": "k_q2_stage", "panel_qr": "k_panel_gram"}.get(dom, dom)
+            roof = {"bound": "tensor", "kernel": famname, "achieved": tf(fl_q2, "q2_stage") if dom == "q2_stage" else None, "peak": dmma_peak,
+                    "unit": "TFLOP/s", "frac": None, "traffic": None}
+            if roof["achieved"]:
+                roof["frac"] = roof["achieved"] / dmma_peak
+        roof["kernel_ms_instrumented_pass"] = {k: round(v["ms"], 3) for k, v in kt.items()}
+        roof["kernel_launches"] = {k: v["launches"] for k, v in kt.items()}
+        roof["largest_family_by_device_time"] = dom
+        roof["kernels"] = kernels
+        roof["fp64_tensor_peak_tflops"] = dmma_peak
+        # -- the step's contractions on their real shapes (not a synthetic GEMM): on-device span timers of the last call
+        f_step, f_expv = contraction_flops(CHI, D_IPEPS ** 2, S_PHYS)
+        cms = timing["contractions"]
+        ctf = (f_step * steps_done + f_expv) / (cms * 1e-3) / 1e12 if cms > 0 else None
+        contractions = {"flops_per_step": f_step, "flops_expectationvalue": f_expv, "ms": cms, "steps": steps_done,
+                        "tflops": ctf, "frac_of_dmma_peak": ctf / dmma_peak if (ctf and dmma_peak) else None,
+                        "what": "forward contractions of all ctmrgsteps + expectationvalue of one energy call (optimal-order flop count, "
+                                "SURVEY.md 8d), timed by CUDA events around the einsum chains"}
+        # -- CPU baseline on a bounded sample (same box, same run) and parity of the GPU result at that sample
+        cpu, parity = None, None
+        if not (args.no_cpu_baseline or world > 1):      # the CPU baseline is measured on rank 0 at N = 1 only
+            bm = args.cpu_maxit
+            cdt, cns, ce, cg = cpu_reference_sample(bm)
+            cpu = {"value": cdt / cns, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                   "sample": f"oracle port (OpenBLAS dgemm + LAPACK dgesdd) energy+gradient, same tensor and chi, maxit={bm} ({cns} steps, {cdt:.1f} s)"}
+            ge, gg = ctx.energy(hh, Ah, CHI, 0.0, bm, grad=True)
+            parity = {"maxit": bm, "energy_gpu": ge, "energy_cpu": ce, "energy_rel_err": abs(ge - ce) / abs(ce),
+                      "grad_rel_err": float(np.linalg.norm(gg - cg) / np.linalg.norm(cg)),
+                      "ok": bool(abs(ge - ce) <= 1e-10 * abs(ce) and np.linalg.norm(gg - cg) <= 1e-8 * np.linalg.norm(cg))}
+        trg64 = None
+        if world == 1 and not args.no_trg:
             try:
-                from threadpoolctl import threadpool_info
-                nthreads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-            except Exception:
-                nthreads = os.cpu_count() or 1
-            cpu = {"value": cdt / cns, "unit": UNIT, "cores": int(nthreads), "kind": "port",
-                   "sample": f"oracle port (OpenBLAS dgemm + LAPACK dgesdd) energy+gradient, same tensor and chi, maxit={args.ref_maxit} ({cns} steps, {cdt:.1f} s)"}
+                trg64 = measure_trg_chi64(ctx, T)
+            except Exception as ex:   # noqa: BLE001
+                trg64 = {"error": repr(ex)}
         total_units = args.steps * steps_done * world
         line = {
             "metric": METRIC, "value": ms * 1e-3 / total_units, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -337,10 +413,15 @@ def run_ours(args):
             "gpu_launches": launches_total,
             "clocks": sampler.summary(),
             "roofline": roof,
+            "contractions": contractions,
             "cpu_baseline": cpu,
+            "parity_check": parity,
+            "trg_chi64_iters_per_s": trg64["iters_per_s"] if trg64 and "iters_per_s" in trg64 else None,
+            "trg_chi64": trg64,
             "breakdown_ms_last_call": {k: round(v, 3) for k, v in timing.items()},
             "energy": e_last,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     dist.barrier()
     for p in (hp, Ap, gp):
@@ -357,8 +438,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--maxit", type=int, default=MAXIT)
-    ap.add_argument("--ref-maxit", type=int, default=1, help="bounded CPU sample: maxit of the oracle run")
+    ap.add_argument("--ref-maxit", type=int, default=None, help="reference arm: maxit of the oracle run (default: --maxit, same config)")
+    ap.add_argument("--cpu-maxit", type=int, default=3, help="our arm: maxit of the bounded CPU baseline sample / parity check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-trg", action="store_true", help="skip the TRG chi=64 part of the metric")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -25,6 +25,52 @@ sys.path.insert(0, ROOT)
 from bench import Dist  # noqa: E402
 
 
+def measure(dist, ctx, d=5, chi=256, steps=3, warmup=1, check=False):
+    """chi-sharded forward ctmrgstep on dist.world GPUs: max-over-ranks device time per step and its split."""
+    import torch
+    import tnad_b200 as T
+    from tnad_b200.sharded import ShardedCTMRG
+    torch.cuda.set_device(dist.local_rank)
+    D = d * d
+    rng = np.random.default_rng(17)                       # same inputs on every rank
+    a = rng.standard_normal((d,) * 4 + (2,))
+    ipeps = T.indexperm_symmetrize(T.SquareIPEPS(a))
+    bulk = np.einsum("abcdx,ijklx->aibjckdl", ipeps.bulk, ipeps.bulk).reshape((D, D, D, D), order="F")
+    bulk /= np.linalg.norm(bulk)
+    corner = rng.standard_normal((chi, chi)); corner += corner.T
+    edge = rng.standard_normal((chi, D, chi)); edge += edge.transpose(2, 1, 0)
+    sh = ShardedCTMRG(ctx, chi, D, dist.dist if dist.on else None)
+    sh.load(bulk, corner, edge)
+    for _ in range(warmup):
+        sh.step()
+        sh.advance()
+    agg = {"contract": 0.0, "gather": 0.0, "svd": 0.0}
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sh.step(timing=True)
+        sh.advance()
+        for k in agg:
+            agg[k] += sh.ms[k]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = dist.max(e0.elapsed_time(e1)) / steps
+    parts = {k: dist.max(v) / steps for k, v in agg.items()}
+    diff = None
+    if check:
+        sh.load(bulk, corner, edge)
+        sh.step()
+        cg, eg, vg = sh.result()
+        c1, e1_, v1 = ctx.ctmrgstep(bulk, corner, edge)
+        diff = dist.max(float(max(np.abs(vg - v1).max(), np.abs(cg - c1).max(), np.abs(eg - e1_).max())))
+    n = chi * D
+    return {"s_per_step": ms * 1e-3, "ms_contract": parts["contract"], "ms_gather": parts["gather"], "ms_svd": parts["svd"],
+            "gather_bytes_per_step": 8 * (n * n + chi * chi + chi * D * chi), "check_max_abs_diff_vs_unsharded": diff,
+            "workload": f"ctmrgstep forward, d={d} (D={D}), chi={chi}, n={n}",
+            "parallelism": f"chi-sharded contractions over {dist.world} GPUs, NCCL all-gather, replicated eigen-decomposition"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -34,58 +80,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
-    import torch
     import tnad_b200 as T
-    from tnad_b200.sharded import ShardedCTMRG
     dist = Dist()
-    torch.cuda.set_device(dist.local_rank)
     ctx = T.Context(dist.local_rank)
-    D, chi = args.d * args.d, args.chi
-    rng = np.random.default_rng(17)                       # same inputs on every rank
-    a = rng.standard_normal((args.d,) * 4 + (2,))
-    ipeps = T.indexperm_symmetrize(T.SquareIPEPS(a))
-    bulk = np.einsum("abcdx,ijklx->aibjckdl", ipeps.bulk, ipeps.bulk).reshape((D, D, D, D), order="F")
-    bulk /= np.linalg.norm(bulk)
-    corner = rng.standard_normal((chi, chi)); corner += corner.T
-    edge = rng.standard_normal((chi, D, chi)); edge += edge.transpose(2, 1, 0)
-    sh = ShardedCTMRG(ctx, chi, D, dist.dist if dist.on else None)
-    sh.load(bulk, corner, edge)
-    for _ in range(args.warmup):
-        sh.step()
-        sh.advance()
-    agg = {"contract": 0.0, "gather": 0.0, "svd": 0.0}
-    sweeps = []
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        sh.step(timing=True)
-        sh.advance()
-        for k in agg:
-            agg[k] += sh.ms[k]
-        sweeps.append(sh.sweeps)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = dist.max(e0.elapsed_time(e1)) / args.steps
-    parts = {k: dist.max(v) / args.steps for k, v in agg.items()}
-    diff = None
-    if args.check:
-        sh.load(bulk, corner, edge)
-        sh.step()
-        cg, eg, vg = sh.result()
-        c1, e1_, v1 = ctx.ctmrgstep(bulk, corner, edge)
-        diff = dist.max(float(max(np.abs(vg - v1).max(), np.abs(np.abs(cg) - np.abs(c1)).max(),
-                                  np.abs(np.abs(eg) - np.abs(e1_)).max())))
+    r = measure(dist, ctx, args.d, args.chi, args.steps, args.warmup, args.check)
     if dist.rank == 0:
-        n = chi * D
         print(json.dumps({
-            "metric": "sharded_ctmrgstep_seconds", "value": ms * 1e-3, "unit": "s/step", "n_gpus": dist.world,
+            "metric": "sharded_ctmrgstep_seconds", "value": r["s_per_step"], "unit": "s/step", "n_gpus": dist.world,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": False, "scaling": "strong", "dtype": "f64",
-            "data": "synthetic", "config": {"workload": f"ctmrgstep forward, d={args.d} (D={D}), chi={chi}, n={n}",
-                                            "parallelism": f"chi-sharded contractions over {dist.world} GPUs, NCCL all-gather, replicated SVD"},
-            "ms_contract": parts["contract"], "ms_gather": parts["gather"], "ms_svd": parts["svd"], "svd_sweeps": sweeps,
-            "gather_bytes_per_step": 8 * (n * n + chi * chi + chi * D * chi),
-            "check_max_abs_diff_vs_unsharded": diff,
+            "data": "synthetic", "config": {"workload": r["workload"], "parallelism": r["parallelism"]},
+            "ms_contract": r["ms_contract"], "ms_gather": r["ms_gather"], "ms_svd": r["ms_svd"],
+            "gather_bytes_per_step": r["gather_bytes_per_step"],
+            "check_max_abs_diff_vs_unsharded": r["check_max_abs_diff_vs_unsharded"],
         }), flush=True)
     dist.barrier()
     ctx.close()

@@ -205,12 +205,14 @@ TNAD_API int tnad_host_free(tnad_ctx* ctx, double* hptr);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of ctx is launched on) */
 TNAD_API int tnad_timer_start(tnad_ctx* ctx);
 TNAD_API int tnad_timer_stop(tnad_ctx* ctx, double* ms);
-/* per-kernel-family device time: enable, run, then read.  families: 0 jacobi_gram (one-sided Jacobi only),
- * 1 eigensolver panel / chase / pivot kernels (the latency-bound kernels of whichever symmetric solver ran),
- * 2 jacobi_update, 3 gemm (every contraction and every GEMM inside the eigensolver), 4 other.
+/* per-kernel-family device time: enable, run, then read (16 slots).  families: 0 jacobi_gram, 1 one-stage
+ * tridiagonalisation panel / Jacobi pivot kernels, 2 jacobi_update, 3 gemm_dmma (every einsum contraction and the GEMMs
+ * of the back-transformation and of the divide and conquer), 4 other, 5/6 work counters of the Jacobi kernels,
+ * 7 k_chase (band -> tridiagonal), 8 k_q2_stage (back-transformation with Q2), 9 k_panel_gram / k_panel_qr (panel QR of the
+ * band reduction), 10 k_symm_y (+ k_reduce_g), 11 k_rank64_update, 12 divide-and-conquer kernels other than its GEMMs.
  * ms[i] = summed duration, count[i] = launches. */
 TNAD_API int tnad_set_kernel_timing(tnad_ctx* ctx, int enable);
-TNAD_API int tnad_kernel_timing(tnad_ctx* ctx, double* ms /* [8] */, int64_t* count /* [8] */);
+TNAD_API int tnad_kernel_timing(tnad_ctx* ctx, double* ms /* [16] */, int64_t* count /* [16] */);
 /* FP64 tensor-core (DMMA m8n8k4) issue-rate microbenchmark: register-resident operands, no memory
  * traffic.  The measured TFLOP/s is the denominator of the `tensor` roofline (MEASURED_PEAKS.json
  * has no FP64 figure). */

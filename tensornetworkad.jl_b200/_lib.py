@@ -203,11 +203,12 @@ class Context:
         self.check(self.lib.tnad_set_kernel_timing(self.h, 1 if enable else 0))
 
     def kernel_timing(self):
-        ms = (C.c_double * 8)()
-        cnt = (C.c_int64 * 8)()
+        ms = (C.c_double * 16)()
+        cnt = (C.c_int64 * 16)()
         self.check(self.lib.tnad_kernel_timing(self.h, ms, cnt))
-        names = ["m_update", "eig_panel", "q_update", "gemm", "other"]
-        out = {n: dict(ms=ms[i], launches=int(cnt[i])) for i, n in enumerate(names)}
+        names = {0: "m_update", 1: "eig_panel", 2: "q_update", 3: "gemm", 4: "other", 7: "chase", 8: "q2_stage",
+                 9: "panel_qr", 10: "symm_y", 11: "rank64_update", 12: "stedc"}
+        out = {n: dict(ms=ms[i], launches=int(cnt[i])) for i, n in names.items()}
         out["m_update"]["blocks"] = int(cnt[5])     # executed 64x64 two-sided block updates (2 x 2*64^3 flop each)
         out["q_update"]["slabs"] = int(cnt[6])      # executed 128x64 panel rotations (2*128*64*64 flop each)
         return out

@@ -1469,7 +1469,7 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   cfg.attrs = at;
   cfg.numAttrs = 2;
   {
-    KTimer kt(c, KF_EIG);
+    KTimer kt(c, KF_CHASE);
     cudaError_t le = cudaLaunchKernelEx(&cfg, k_chase, a);
     if (le != cudaSuccess) {   // co-residency cannot be promised together with this cluster shape: the mailbox time-out still guards
       cudaGetLastError();
@@ -1519,7 +1519,7 @@ void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, in
     a.lds = lds;
     // the first slot of the stage is active for sweeps s <= n - 2 - 32 q0 only: later (= earlier in time) sweeps are skipped
     a.s_top = (int)std::min<int64_t>(s_top, ((n - 1 - (int64_t)CB * a.q0) + 31) / 32 * 32 - 1);
-    KTimer kt(c, KF_UPDATE);
+    KTimer kt(c, KF_Q2);
     k_q2_stage<<<grid, Q2_NT, 0, c->stream>>>(a);
     LAUNCH_CHECK(c);
   }
@@ -1611,7 +1611,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
         at[0].val.clusterDim.x = gcs;
         cg_.attrs = at;
         cg_.numAttrs = 1;
-        KTimer kt(c, KF_EIG);
+        KTimer kt(c, KF_PANEL);
         if (gnrl == 1) TNAD_CUDA(cudaLaunchKernelEx(&cg_, k_panel_gram<1>, pg, fbp));
         else TNAD_CUDA(cudaLaunchKernelEx(&cg_, k_panel_gram<2>, pg, fbp));
         c->launches++;
@@ -1629,7 +1629,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     {
-      KTimer kt(c, KF_EIG);
+      KTimer kt(c, KF_PANEL);
       if (regs && nrl == 1) TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr<1>, pa));
       else if (regs) TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr<2>, pa));
       else TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr<0>, pa));
@@ -1643,7 +1643,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ksplit_max, (2 * c->num_sms + nrb - 1) / nrb));
     ksplit = (int)std::min<int64_t>(ksplit, (m + 4 * SY_BK - 1) / (4 * SY_BK));
     {
-      KTimer kt(c, KF_GEMM);
+      KTimer kt(c, KF_SYMM);
       k_symm_y<<<dim3(nrb, ksplit), 128, 2 * SY_STAGE * sizeof(double), st>>>(A22p, lda, Yp, ldy, (int)m, ksplit, Zp.p, n, Gp.p,
                                                                                     (n % 2 == 0 && lda % 2 == 0 && ldy % 2 == 0) ? 1 : 0);
       LAUNCH_CHECK(c);
@@ -1655,7 +1655,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     LAUNCH_CHECK(c);
     if (prof) TNAD_CUDA(cudaEventRecord(pe[3], st));
     {
-      KTimer kt(c, KF_GEMM);
+      KTimer kt(c, KF_RANK64);
       const int nt = (int)((m + 63) / 64);
       k_rank64_update<<<dim3(nt, nt), 128, 2 * 64 * RU_LD * sizeof(double), st>>>(A22p, lda, P1.p, P2.p, ldpp, (int)m);
     }

@@ -179,7 +179,8 @@ struct Span {
   ~Span();
 };
 // RAII bracket around one kernel launch for the per-family device-time table (no-op unless enabled)
-enum KFam { KF_GRAM = 0, KF_EIG = 1, KF_UPDATE = 2, KF_GEMM = 3, KF_OTHER = 4 };
+enum KFam { KF_GRAM = 0, KF_EIG = 1, KF_UPDATE = 2, KF_GEMM = 3, KF_OTHER = 4,
+            KF_CHASE = 7, KF_Q2 = 8, KF_PANEL = 9, KF_SYMM = 10, KF_RANK64 = 11, KF_STEDC = 12, KF_NFAM = 16 };
 struct KTimer {
   tnad_ctx* c;
   int fam;

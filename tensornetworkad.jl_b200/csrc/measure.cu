@@ -101,13 +101,13 @@ int tnad_kernel_timing(tnad_ctx* c, double* ms, int64_t* count) {
   API_BEGIN(c)
   TNAD_REQUIRE(ms && count, "tnad_kernel_timing: null output");
   sync(c);
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < KF_NFAM; ++i) {
     ms[i] = 0.0;
     count[i] = 0;
   }
   for (auto& k : c->kspans) {
     float f = 0.f;
-    if (cudaEventElapsedTime(&f, k.a, k.b) == cudaSuccess && k.fam >= 0 && k.fam < 8) {
+    if (cudaEventElapsedTime(&f, k.a, k.b) == cudaSuccess && k.fam >= 0 && k.fam < KF_NFAM) {
       ms[k.fam] += f;
       count[k.fam] += 1;
     }

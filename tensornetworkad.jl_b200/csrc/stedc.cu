@@ -594,7 +594,7 @@ void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam
     const int se = s + (s & 1);
     const size_t smem = (size_t)(2 * se * (se + 1) + se + 8) * sizeof(double);
     TNAD_CUDA(cudaFuncSetAttribute(k_dc_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KTimer kt(c, KF_OTHER);
+    KTimer kt(c, KF_STEDC);
     k_dc_leaf<<<(int)(N / s), 256, smem, st>>>(dp.p, ep.p, s, (int)N, lamA.p, Qa.p, N);
     c->launches++;
     TNAD_CUDA(cudaGetLastError());
@@ -628,12 +628,12 @@ void stedc(tnad_ctx* c, const double* dd, const double* ee, int64_t n, Tens& lam
       k_dc_z<<<dim3((m2 + 255) / 256, G), 256, 0, st>>>(Qin->p, N, beta.p, m, zu.p, rho.p);
       k_dc_sort<<<dim3((m2 + 255) / 256, G), 256, 0, st>>>(lam_in, zu.p, m2, order, ds.p, zs.p);
       {
-        KTimer kt(c, KF_OTHER);
+        KTimer kt(c, KF_STEDC);
         k_dc_deflate<<<G, 256, 0, st>>>(m2, rho.p, ds.p, zs.p, order, ndl, dfl, rotp, rotj, rotc.p, rots.p, dn.p, zn.p, meta);
       }
       if (debug) TNAD_CUDA(cudaEventRecord(e1, st));
       {
-        KTimer kt(c, KF_OTHER);
+        KTimer kt(c, KF_STEDC);
         k_dc_secular<<<dim3((m2 + 3) / 4, G), 128, 0, st>>>(m2, rho.p, dn.p, zn.p, meta, Dl.p, ldd, lam_out);
       }
       if (debug) TNAD_CUDA(cudaEventRecord(e2, st));

@@ -1307,7 +1307,7 @@ static void eigh_dc(tnad_ctx* c, Tens& Aw, int64_t n, std::vector<double>& lh, T
   const bool debug = opt_i(c, "TNAD_DC_DEBUG", 0) != 0;
   // two-stage route (band.cu) from n >= TNAD_2STAGE_MIN on; TNAD_EIG_2STAGE = 0 | 1 forces one route
   const int ts_mode = opt_i(c, "TNAD_EIG_2STAGE", -1);
-  const bool two_stage = n >= 67 && (ts_mode == 1 || (ts_mode < 0 && n >= opt_i(c, "TNAD_2STAGE_MIN", 768)));
+  const bool two_stage = n >= 67 && (ts_mode == 1 || (ts_mode < 0 && n >= opt_i(c, "TNAD_2STAGE_MIN", 512)));
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (debug)
     for (auto& e : ev) e = get_event(c);
