@@ -183,6 +183,18 @@ TNAD_API int tnad_trg_sweep(const double* tensors, int ninst, int d0, int d1, in
 /* ---- pieces used by the chi-sharded multi-GPU step (tensornetworkad.jl_b200/sharded.py) -------- */
 /* svd(A + A') for a square A (ctmrg.jl:133-135: `cpmat += adjoint(cpmat); svd(cpmat)`), same solver as tnad_svd_sym */
 TNAD_API int tnad_svd_symmetrized(tnad_ctx* ctx, const double* A, int n, double* U, double* S, double* V, int* sweeps_out);
+/* The symmetric eigensolver behind tnad_svd_sym / tnad_svd_symmetrized in three phases, so that several GPUs can
+ * share its back-transformation (the chi-sharded step: every rank reduces the replicated matrix, back-transforms its
+ * own block of columns, the blocks are all-gathered, every rank finishes):
+ *   reduce         A (+ A' if add_transpose) -> tridiagonal (one- or two-stage) and its eigen-decomposition;
+ *                  *N_out = padded order N >= n of the eigenvector matrix
+ *   backtransform  Zcols (N x ncols, leading dimension N) = columns col0 .. col0+ncols-1 of Q Z
+ *   finish         Zfull (N x N, all columns back-transformed) -> U, S, V as tnad_svd_sym returns them */
+typedef struct tnad_eig tnad_eig;
+TNAD_API int tnad_symeig_reduce(tnad_ctx* ctx, const double* A, int n, int add_transpose, tnad_eig** out, int* N_out);
+TNAD_API int tnad_symeig_backtransform(tnad_ctx* ctx, tnad_eig* h, int col0, int ncols, double* Zcols);
+TNAD_API int tnad_symeig_finish(tnad_ctx* ctx, tnad_eig* h, const double* Zfull, double* U, double* S, double* V);
+TNAD_API int tnad_symeig_free(tnad_eig* h);
 /* stages of the direct symmetric eigensolver (tridiag.cu / stedc.cu), exported for the parity tests:
    A = Q T Q' with T = tridiag(d, e) (Householder, LAPACK dsytrd semantics; Q explicit n x n) ... */
 TNAD_API int tnad_sytrd(tnad_ctx* ctx, const double* A, int n, double* d, double* e, double* Q);

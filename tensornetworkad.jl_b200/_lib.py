@@ -73,6 +73,10 @@ SIGNATURES = {
                                  c_int_p, c_double_p, C.c_void_p, C.c_char_p, C.c_int]),
     "tnad_svd_symmetrized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p]),
     "tnad_sytrd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tnad_symeig_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_int_p]),
+    "tnad_symeig_backtransform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tnad_symeig_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tnad_symeig_free": (C.c_int, [C.c_void_p]),
     "tnad_sytrd2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tnad_stedc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_permute": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, c_int_p, C.c_void_p]),
@@ -459,6 +463,22 @@ class Context:
         self.check(self.lib.tnad_svd_symmetrized(self.h, C.c_void_p(pa), int(n), C.c_void_p(pu), C.c_void_p(ps), C.c_void_p(pv),
                                          C.byref(sw)))
         return sw.value
+
+    # three-phase symmetric eigensolver on device pointers (the back-transformation is shared between ranks)
+    def dev_symeig_reduce(self, pa, n, add_transpose=True):
+        h = C.c_void_p()
+        N = C.c_int(0)
+        self.check(self.lib.tnad_symeig_reduce(self.h, C.c_void_p(pa), int(n), 1 if add_transpose else 0, C.byref(h), C.byref(N)))
+        return h, N.value
+
+    def dev_symeig_backtransform(self, h, col0, ncols, pz):
+        self.check(self.lib.tnad_symeig_backtransform(self.h, h, int(col0), int(ncols), C.c_void_p(pz)))
+
+    def dev_symeig_finish(self, h, pzfull, pu, ps, pv):
+        self.check(self.lib.tnad_symeig_finish(self.h, h, C.c_void_p(pzfull), C.c_void_p(pu), C.c_void_p(ps), C.c_void_p(pv)))
+
+    def symeig_free(self, h):
+        self.lib.tnad_symeig_free(h)
 
     def dev_ctmrg_finish(self, pc1, pe1, D, chi, pco, peo):
         self.check(self.lib.tnad_ctmrg_finish(self.h, C.c_void_p(pc1), C.c_void_p(pe1), int(D), int(chi),

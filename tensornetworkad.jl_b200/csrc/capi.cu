@@ -256,6 +256,71 @@ int tnad_svd_symmetrized(tnad_ctx* c, const double* A, int n, double* U, double*
   TNAD_API_END(c)
 }
 
+// ---- the symmetric eigensolver in three phases (the back-transformation is independent per column: GPUs share it) ----
+struct tnad_eig {
+  tnad_ctx* ctx = nullptr;
+  tnad::EigFactor f;
+};
+
+int tnad_symeig_reduce(tnad_ctx* c, const double* A, int n, int add_transpose, tnad_eig** out, int* N_out) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(A && n >= 1 && out && N_out, "tnad_symeig_reduce: bad arguments");
+  TNAD_REQUIRE(c->coop_launch, "tnad_symeig_reduce: needs cooperative kernel launches");
+  Tens tA = t_in(c, A, {n, n});
+  Tens Aw;
+  load_symmetric(c, tA, add_transpose != 0, Aw);
+  tnad_eig* h = new tnad_eig();
+  h->ctx = c;
+  try {
+    symeig_reduce(c, Aw, n, h->f);
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  sync(c);
+  *out = h;
+  *N_out = (int)h->f.N;
+  TNAD_API_END(c)
+}
+
+int tnad_symeig_backtransform(tnad_ctx* c, tnad_eig* h, int col0, int ncols, double* Zcols) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(h && h->ctx == c && Zcols && col0 >= 0 && ncols >= 0 && col0 + ncols <= h->f.N, "tnad_symeig_backtransform: bad arguments");
+  const int64_t N = h->f.N;
+  if (c->pointer_mode == TNAD_POINTER_DEVICE) {
+    TNAD_CUDA(cudaMemcpyAsync(Zcols, h->f.Z.p + (int64_t)col0 * N, (size_t)N * ncols * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    symeig_backtransform(c, h->f, Zcols, N, ncols);
+    sync(c);
+  } else {
+    Tens tmp = t_alloc(c, {N, (int64_t)ncols});
+    TNAD_CUDA(cudaMemcpyAsync(tmp.p, h->f.Z.p + (int64_t)col0 * N, (size_t)N * ncols * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    symeig_backtransform(c, h->f, tmp.p, N, ncols);
+    t_out(c, tmp, Zcols);
+  }
+  TNAD_API_END(c)
+}
+
+int tnad_symeig_finish(tnad_ctx* c, tnad_eig* h, const double* Zfull, double* U, double* S, double* V) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(h && h->ctx == c && Zfull && U && S && V, "tnad_symeig_finish: bad arguments");
+  Tens tZ = t_in(c, Zfull, {h->f.N, h->f.N});
+  SvdResult r = symeig_finish(c, h->f, tZ.p);
+  t_out(c, r.U, U);
+  t_out(c, r.S, S);
+  t_out(c, r.V, V);
+  TNAD_API_END(c)
+}
+
+int tnad_symeig_free(tnad_eig* h) {
+  if (!h) return TNAD_OK;
+  if (h->ctx) {
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+  }
+  delete h;
+  return TNAD_OK;
+}
+
 int tnad_sytrd(tnad_ctx* c, const double* A, int n, double* d, double* e, double* Q) {
   TNAD_API_BEGIN(c)
   TNAD_REQUIRE(n >= 1 && d && e && Q, "tnad_sytrd: bad arguments");

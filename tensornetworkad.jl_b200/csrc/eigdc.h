@@ -21,6 +21,19 @@ void extract_band(tnad_ctx* c, const double* A, int64_t lda, int64_t n, double* 
 void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t ldy, double* tau1);
 void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, double* ee, double* V2, int64_t ldv, double* tau2);
 void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, int64_t n, double* X, int64_t ldx, int64_t ncols);
+// three-phase form of the direct symmetric eigensolver (reduce / back-transform a column block / finish)
+struct EigFactor {
+  int64_t n = 0, N = 0, ldv2 = 0;
+  bool two_stage = false;
+  Tens Vh, tau;          // reflectors of the (first) reduction stage
+  Tens V2, tau2;         // reflectors of the chase (two-stage route)
+  Tens Z;                // eigenvectors of the tridiagonal matrix (N x N, N >= n padded)
+  std::vector<double> lam;
+};
+void load_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, Tens& Aw);
+void symeig_reduce(tnad_ctx* c, Tens& Aw, int64_t n, EigFactor& f);
+void symeig_backtransform(tnad_ctx* c, const EigFactor& f, double* Zc, int64_t ldz, int64_t ncols);
+SvdResult symeig_finish(tnad_ctx* c, const EigFactor& f, const double* Zfull);
 SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose);
 // general (rank-2 or rank-4 [(d1,d2),(d3,d4)] view) matrix through the Jordan-Wielandt embedding; only the r non-null
 // triplets are formed (rank_left = rank_right = r)

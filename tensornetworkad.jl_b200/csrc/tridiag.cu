@@ -1289,10 +1289,12 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
   }
 }
 
-// Eigen-decomposition route: tridiagonalise, divide and conquer, back-transform.
-// Eigen-decomposition of the symmetric matrix in Aw (n x n contiguous, overwritten): eigenvalues to the host (lh, N
-// entries incl. the pads, already rescaled), eigenvectors as columns of Z (N x N, leading dimension N; rows >= n are pad rows).
-static void eigh_dc(tnad_ctx* c, Tens& Aw, int64_t n, std::vector<double>& lh, Tens& Z, int64_t& N) {
+// Eigen-decomposition route in three phases (the split lets several GPUs share the back-transformation, see
+// tnad_symeig_* in capi.cu and tensornetworkad.jl_b200/sharded.py):
+//   reduce          A -> tridiagonal T (one- or two-stage) and the eigen-decomposition of T by divide and conquer
+//   backtransform   columns [col0, col0 + ncols) of Z <- Q Z   (independent per column)
+//   finish          sort by |lambda|, V = U sign(lambda), canonical column signs
+void symeig_reduce(tnad_ctx* c, Tens& Aw, int64_t n, EigFactor& f) {
   cudaStream_t st = c->stream;
   // scale to max|a_ij| = 1 (the reflector norms are plain sums of squares; LAPACK rescales inside dlarfg instead)
   double amax = 0.0;
@@ -1303,75 +1305,83 @@ static void eigh_dc(tnad_ctx* c, Tens& Aw, int64_t n, std::vector<double>& lh, T
     if (amax > 0.0 && std::isfinite(amax)) scale_dev(c, Aw, Aw, sc.p, SC_INV);
     else amax = 1.0;
   }
-  Tens Vh = t_alloc(c, {n, sytrd_vcols(n)}, true), tau = t_alloc(c, {sytrd_vcols(n)}, true), dd = t_alloc(c, {n}), ee = t_alloc(c, {n}, true);
+  f.n = n;
+  f.Vh = t_alloc(c, {n, sytrd_vcols(n)}, true);
+  f.tau = t_alloc(c, {sytrd_vcols(n)}, true);
+  Tens dd = t_alloc(c, {n}), ee = t_alloc(c, {n}, true);
   const bool debug = opt_i(c, "TNAD_DC_DEBUG", 0) != 0;
   // two-stage route (band.cu) from n >= TNAD_2STAGE_MIN on; TNAD_EIG_2STAGE = 0 | 1 forces one route
   const int ts_mode = opt_i(c, "TNAD_EIG_2STAGE", -1);
-  const bool two_stage = n >= 67 && (ts_mode == 1 || (ts_mode < 0 && n >= opt_i(c, "TNAD_2STAGE_MIN", 512)));
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  f.two_stage = n >= 67 && (ts_mode == 1 || (ts_mode < 0 && n >= opt_i(c, "TNAD_2STAGE_MIN", 512)));
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (debug)
     for (auto& e : ev) e = get_event(c);
   if (debug) TNAD_CUDA(cudaEventRecord(ev[0], st));
   Tens lam;
-  if (two_stage) {
-    const int64_t NP = chase_positions(n), ldv2 = 32 * NP;
-    sy2sb(c, Aw.p, n, n, Vh.p, n, tau.p);                      // A = Q1 B Q1'
+  if (f.two_stage) {
+    const int64_t NP = chase_positions(n);
+    f.ldv2 = 32 * NP;
+    sy2sb(c, Aw.p, n, n, f.Vh.p, n, f.tau.p);                      // A = Q1 B Q1'
     Tens AB = t_alloc(c, {33, n});
     extract_band(c, Aw.p, n, n, AB.p, 33);
     if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
-    Tens V2 = t_alloc(c, {ldv2, n - 2}, true), tau2 = t_alloc(c, {NP, n - 2}, true);
-    sb2st(c, AB.p, 33, n, dd.p, ee.p, V2.p, ldv2, tau2.p);     // B = Q2 T Q2'
-    if (debug) TNAD_CUDA(cudaEventRecord(ev[2], st));
-    stedc(c, dd.p, ee.p, n, lam, Z, N);
-    if (debug) TNAD_CUDA(cudaEventRecord(ev[3], st));
-    apply_q2(c, V2.p, ldv2, tau2.p, n, Z.p, N, N);
-    if (debug) TNAD_CUDA(cudaEventRecord(ev[4], st));
-    apply_q(c, Vh.p, n, tau.p, n, Z.p, N, N, 32);
-    if (debug) {
-      TNAD_CUDA(cudaEventRecord(ev[5], st));
-      TNAD_CUDA(cudaEventSynchronize(ev[5]));
-      float t[5];
-      for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-      fprintf(stderr, "[tnad dc] n=%lld N=%lld two-stage: sy2sb %.2f ms  chase %.2f ms  stedc %.2f ms  apply_q2 %.2f ms  apply_q1 %.2f ms\n",
-              (long long)n, (long long)N, t[0], t[1], t[2], t[3], t[4]);
-    }
+    f.V2 = t_alloc(c, {f.ldv2, n - 2}, true);
+    f.tau2 = t_alloc(c, {NP, n - 2}, true);
+    sb2st(c, AB.p, 33, n, dd.p, ee.p, f.V2.p, f.ldv2, f.tau2.p);   // B = Q2 T Q2'
   } else {
-    sytrd(c, Aw.p, n, n, Vh.p, n, tau.p, dd.p, ee.p);
+    sytrd(c, Aw.p, n, n, f.Vh.p, n, f.tau.p, dd.p, ee.p);
     if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
-    stedc(c, dd.p, ee.p, n, lam, Z, N);   // Z: N x N (ld N), lam: N, pads carry eigenvalues above the spectrum
-    if (debug) TNAD_CUDA(cudaEventRecord(ev[2], st));
-    apply_q(c, Vh.p, n, tau.p, n, Z.p, N, N);
-    if (debug) {
-      TNAD_CUDA(cudaEventRecord(ev[3], st));
-      TNAD_CUDA(cudaEventSynchronize(ev[3]));
-      float a = 0, b = 0, d3 = 0;
-      cudaEventElapsedTime(&a, ev[0], ev[1]);
-      cudaEventElapsedTime(&b, ev[1], ev[2]);
-      cudaEventElapsedTime(&d3, ev[2], ev[3]);
-      fprintf(stderr, "[tnad dc] n=%lld N=%lld sytrd %.2f ms  stedc %.2f ms  apply_q %.2f ms\n", (long long)n, (long long)N, a, b, d3);
-    }
   }
-  if (debug)
+  if (debug) TNAD_CUDA(cudaEventRecord(ev[2], st));
+  stedc(c, dd.p, ee.p, n, lam, f.Z, f.N);   // Z: N x N (ld N), lam: N, pads carry eigenvalues above the spectrum
+  if (debug) {
+    TNAD_CUDA(cudaEventRecord(ev[3], st));
+    TNAD_CUDA(cudaEventSynchronize(ev[3]));
+    float t[3];
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+    if (f.two_stage)
+      fprintf(stderr, "[tnad dc] n=%lld N=%lld two-stage: sy2sb %.2f ms  chase %.2f ms  stedc %.2f ms", (long long)n, (long long)f.N, t[0], t[1], t[2]);
+    else
+      fprintf(stderr, "[tnad dc] n=%lld N=%lld sytrd %.2f ms  stedc %.2f ms", (long long)n, (long long)f.N, t[0] + t[1], t[2]);
     for (auto& e : ev) c->event_pool.push_back(e);
-  lh.resize((size_t)N);
-  d2h(c, lh.data(), lam.p, (size_t)N);
-  for (auto& v : lh) v *= amax;
+  }
+  f.lam.resize((size_t)f.N);
+  d2h(c, f.lam.data(), lam.p, (size_t)f.N);
+  for (auto& v : f.lam) v *= amax;
 }
 
-// Eigen-decomposition route: tridiagonalise, divide and conquer, back-transform.
-SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
-  TNAD_REQUIRE(A.rank == 2 && A.dim[0] == A.dim[1], "svd_symmetric_dc: need a square matrix");
-  const int64_t n = A.dim[0];
+// Zc (N x ncols, leading dimension ldz) holds columns col0.. of the tridiagonal eigenvectors on entry, of Q times them on exit
+void symeig_backtransform(tnad_ctx* c, const EigFactor& f, double* Zc, int64_t ldz, int64_t ncols) {
+  const bool debug = opt_i(c, "TNAD_DC_DEBUG", 0) != 0;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (debug) {
+    for (auto& e : ev) e = get_event(c);
+    TNAD_CUDA(cudaEventRecord(ev[0], c->stream));
+  }
+  if (f.two_stage) {
+    apply_q2(c, f.V2.p, f.ldv2, f.tau2.p, f.n, Zc, ldz, ncols);
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[1], c->stream));
+    apply_q(c, f.Vh.p, f.n, f.tau.p, f.n, Zc, ldz, ncols, 32);
+  } else {
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[1], c->stream));
+    apply_q(c, f.Vh.p, f.n, f.tau.p, f.n, Zc, ldz, ncols);
+  }
+  if (debug) {
+    TNAD_CUDA(cudaEventRecord(ev[2], c->stream));
+    TNAD_CUDA(cudaEventSynchronize(ev[2]));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    fprintf(stderr, "  apply_q2 %.2f ms  apply_q1 %.2f ms  (%lld columns)\n", a, b, (long long)ncols);
+    for (auto& e : ev) c->event_pool.push_back(e);
+  }
+}
+
+// Zfull: the back-transformed N x N eigenvector matrix (ld N).  U, S, V as LinearAlgebra.svd returns them for a symmetric matrix.
+SvdResult symeig_finish(tnad_ctx* c, const EigFactor& f, const double* Zfull) {
+  const int64_t n = f.n, N = f.N;
   cudaStream_t st = c->stream;
-  Tens Aw = t_alloc(c, {n, n});
-  const int nbk = (int)std::max<long long>(1, std::min<long long>((n * n + 1023) / 1024, 148 * 8));
-  k_load_symm<<<nbk, 256, 0, st>>>(Aw.p, n, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
-  c->launches++;
-  TNAD_CUDA(cudaGetLastError());
-  std::vector<double> lh;
-  Tens Z;
-  int64_t N = 0;
-  eigh_dc(c, Aw, n, lh, Z, N);
+  const std::vector<double>& lh = f.lam;
   // the N - n pad eigenvalues are the largest ones (stedc puts them above 3 |T|)
   std::vector<int> idx((size_t)N);
   for (int64_t i = 0; i < N; ++i) idx[(size_t)i] = (int)i;
@@ -1396,7 +1406,7 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
   res.U = t_alloc(c, {n, n});
   res.V = t_alloc(c, {n, n});
   res.S = t_alloc(c, {n});
-  k_gather_cols<<<(int)n, 128, 0, st>>>(Z.p, N, dperm, dsgn, n, res.U.p, res.V.p);
+  k_gather_cols<<<(int)n, 128, 0, st>>>(Zfull, N, dperm, dsgn, n, res.U.p, res.V.p);
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
   TNAD_CUDA(cudaMemcpyAsync(res.S.p, dsval, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1405,6 +1415,35 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
   res.null_thr = 16.0 * 2.220446049250313e-16 * std::sqrt(fro2);   // same absolute level as the Jacobi solver
   res.sweeps = 0;
   return res;
+}
+
+void load_symmetric(tnad_ctx* c, const Tens& A, bool sym_add_transpose, Tens& Aw) {
+  TNAD_REQUIRE(A.rank == 2 && A.dim[0] == A.dim[1], "symmetric eigensolver: need a square matrix");
+  const int64_t n = A.dim[0];
+  Aw = t_alloc(c, {n, n});
+  const int nbk = (int)std::max<long long>(1, std::min<long long>((n * n + 1023) / 1024, 148 * 8));
+  k_load_symm<<<nbk, 256, 0, c->stream>>>(Aw.p, n, A.p, A.str[0], A.str[1], n, sym_add_transpose ? 1 : 0);
+  c->launches++;
+  TNAD_CUDA(cudaGetLastError());
+}
+
+static void eigh_dc(tnad_ctx* c, Tens& Aw, int64_t n, std::vector<double>& lh, Tens& Z, int64_t& N) {
+  EigFactor f;
+  symeig_reduce(c, Aw, n, f);
+  symeig_backtransform(c, f, f.Z.p, f.N, f.N);
+  lh = f.lam;
+  Z = f.Z;
+  N = f.N;
+}
+
+// Eigen-decomposition route: tridiagonalise, divide and conquer, back-transform.
+SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
+  Tens Aw;
+  load_symmetric(c, A, sym_add_transpose, Aw);
+  EigFactor f;
+  symeig_reduce(c, Aw, A.dim[0], f);
+  symeig_backtransform(c, f, f.Z.p, f.N, f.N);
+  return symeig_finish(c, f, f.Z.p);
 }
 
 // General m x n matrix through the Jordan-Wielandt embedding H = [0 A; A' 0] (order m + n): the eigenpairs of H are

@@ -108,6 +108,7 @@ class ShardedCTMRG:
         self.buf = {k: torch.empty(v, dtype=torch.float64, device=self.dev) for k, v in buffer_sizes(self.plan).items()}
         self.schedule = step_schedule(self.plan)
         self.sweeps = 0
+        self.split_eig = True          # share the back-transformation of the eigen-decomposition between the ranks
         self.ms = {"contract": 0.0, "gather": 0.0, "svd": 0.0}
 
     # -- helpers ------------------------------------------------------------------------------------------
@@ -155,7 +156,7 @@ class ShardedCTMRG:
                 elif kind == "permute":
                     c.dev_permute(P(op[1]), op[2], op[3], P(op[4]))
                 elif kind == "svd_symmetrized":
-                    self.sweeps = c.dev_svd_symmetrized(P(op[1]), op[2], P(op[3]), P(op[4]), P(op[5]))
+                    self._svd(op, P)
                 elif kind == "finish":
                     c.dev_ctmrg_finish(P(op[1]), P(op[2]), p.D, p.chi, P(op[3]), P(op[4]))
                 else:
@@ -168,6 +169,30 @@ class ShardedCTMRG:
             c.set_pointer_mode(0)
         if timing:
             self.ms = ms
+
+    def _svd(self, op, P):
+        """svd(cp + cp') (ctmrg.jl:134-136).  One rank: one call.  Several ranks: every rank reduces the replicated
+        matrix to tridiagonal form and solves the tridiagonal problem (latency-bound stages), back-transforms ITS block
+        of N / world eigenvector columns (the 2 x 2 n^3 flop of the decomposition), the blocks are all-gathered and
+        every rank sorts / sign-fixes the result."""
+        c, p, B, t = self.ctx, self.plan, self.buf, self.torch
+        n = op[2]
+        if self.dist is None or p.world == 1 or not self.split_eig:
+            self.sweeps = c.dev_svd_symmetrized(P(op[1]), n, P(op[3]), P(op[4]), P(op[5]))
+            return
+        h, N = c.dev_symeig_reduce(P(op[1]), n, True)
+        try:
+            if N % p.world:
+                raise ValueError(f"padded order {N} is not divisible by the number of ranks")
+            wcols = N // p.world
+            if "Zfull" not in B or B["Zfull"].numel() != N * N:
+                B["Zfull"] = t.empty(N * N, dtype=t.float64, device=self.dev)
+                B["Zpart"] = t.empty(N * wcols, dtype=t.float64, device=self.dev)
+            c.dev_symeig_backtransform(h, p.rank * wcols, wcols, B["Zpart"].data_ptr())
+            self._gather(B["Zfull"], B["Zpart"])
+            c.dev_symeig_finish(h, B["Zfull"].data_ptr(), P(op[3]), P(op[4]), P(op[5]))
+        finally:
+            c.symeig_free(h)
 
     def advance(self):
         """Feed the result back as the next environment."""

@@ -837,3 +837,34 @@ def test_energy_gradient_same_with_one_and_two_stage(ctx, opt):
         out[mode] = ctx.energy(h, A, 64, 0.0, 4, grad=True)
     (e1, g1), (e2, g2) = out["0"], out["1"]
     assert abs(e1 - e2) <= 1e-11 * abs(e1) and np.abs(g1 - g2).max() <= 1e-9 * np.abs(g1).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [150, 700])
+def test_symeig_three_phase_matches_single_call(ctx, n):
+    """tnad_symeig_reduce / _backtransform (two column blocks, as two ranks would do) / _finish against tnad_svd_symmetrized."""
+    import torch
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    dev = torch.device("cuda", ctx.device)
+    A = torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).to(dev)
+    U = torch.empty(n * n, dtype=torch.float64, device=dev); V = torch.empty_like(U)
+    S = torch.empty(n, dtype=torch.float64, device=dev)
+    ctx.set_pointer_mode(1)
+    try:
+        h, N = ctx.dev_symeig_reduce(A.data_ptr(), n, True)
+        Z = torch.empty(N * N, dtype=torch.float64, device=dev)
+        half = (N // 2 // 2) * 2
+        ctx.dev_symeig_backtransform(h, 0, half, Z.data_ptr())
+        ctx.dev_symeig_backtransform(h, half, N - half, Z.data_ptr() + 8 * N * half)
+        ctx.dev_symeig_finish(h, Z.data_ptr(), U.data_ptr(), S.data_ptr(), V.data_ptr())
+        ctx.symeig_free(h)
+    finally:
+        ctx.set_pointer_mode(0)
+    u = U.cpu().numpy().reshape((n, n), order="F"); v = V.cpu().numpy().reshape((n, n), order="F"); s = S.cpu().numpy()
+    m = a + a.T
+    ref = np.linalg.svd(m, compute_uv=False)
+    assert np.abs(s - ref).max() <= 1e-12 * ref[0]
+    assert np.abs((u * s) @ v.T - m).max() <= 1e-12 * ref[0]
+    u1, s1, v1 = ctx.svd_sym(m)
+    assert np.abs(s - s1).max() <= 1e-13 * ref[0] and np.abs(u - u1).max() < 1e-9     # same canonical gauge

@@ -390,3 +390,23 @@ def test_golub_kahan_prototype():
         assert np.abs(s - ref).max() < 1e-13 * ref[0]
         assert np.abs((U * s) @ V.T - a).max() < 1e-13 * ref[0]
         assert np.abs(U[:, :r].T @ U[:, :r] - np.eye(r)).max() < 1e-10
+
+
+# ---- two-stage tridiagonalisation: the NumPy statement of the kernels' data flow (tools/twostage_proto.py) ----------
+def test_twostage_proto_direct_and_systolic():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("twostage_proto", os.path.join(ROOT, "tools", "twostage_proto.py"))
+    P = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(P)
+    rng = np.random.default_rng(0)
+    # dense -> band -> tridiagonal -> back-transformation, textbook order
+    for n, b in [(37, 4), (50, 16), (9, 4), (6, 4)]:
+        A = rng.standard_normal((n, n)); A = A + A.T
+        lam, U, (Bd, d, e) = P.eigh_twostage(A, b)
+        assert np.abs(np.tril(Bd, -b - 1)).max() == 0.0
+        assert np.abs(lam - np.linalg.eigvalsh(A)).max() < 1e-12 * np.abs(lam).max()
+        assert np.abs(A @ U - U * lam).max() < 1e-12 * np.abs(lam).max() and np.abs(U.T @ U - np.eye(n)).max() < 1e-13
+    # the systolic formulation the kernels use (windows, mailboxes, zero padding, staged Q2 pass), b = 32
+    for n in (3, 5, 33, 34, 65, 97, 130):
+        err_t, res, orth = P.check_systolic(n, rng)
+        assert res < 1e-12 and orth < 1e-13, (n, res, orth)
