@@ -162,6 +162,15 @@ TNAD_API int tnad_expectationvalue_backward(tnad_ctx* ctx, const double* h, cons
  * exactly as Zygote + src/autodiff.jl compute it.  A is (d,d,d,d,s). steps_done may be NULL. */
 TNAD_API int tnad_energy(tnad_ctx* ctx, const double* h, const double* A, int d, int s, int chi,
                 double tol, int maxit, double* e, double* gradA, int* steps_done);
+/* The same energy with the IMPLICIT (fixed-point) gradient, opt-in: CTMRG runs without a tape until the reference's stop
+ * rule fires, one more step is recorded at the final environment, and the gradient is the Neumann series
+ * sum_k J_a' (J_x')^k xbar of that step's pullback, truncated when the cotangent has decayed by bwd_tol (or after bwd_maxit
+ * terms; *bwd_iters returns the number applied).  Agrees with tnad_energy's gradient -- i.e. with what Zygote computes
+ * for the reference -- in the limit of a converged environment; memory is one step record instead of one per step.
+ * Not what the reference computes for short fixed-maxit runs (it treats the initial environment as a constant). */
+TNAD_API int tnad_energy_fixedpoint(tnad_ctx* ctx, const double* h, const double* A, int d, int s, int chi,
+                           double tol, int maxit, double bwd_tol, int bwd_maxit,
+                           double* e, double* gradA, int* steps_done, int* bwd_iters);
 /* magnetisation read-out (exampletensors.jl:63-68): |<env,m>/<env,a>| */
 TNAD_API int tnad_magnetisation_readout(tnad_ctx* ctx, const double* a, const double* m, int D,
                                const double* corner, const double* edge, int chi, double* mag);

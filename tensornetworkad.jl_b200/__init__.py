@@ -30,7 +30,7 @@ __all__ = [
     "magnetisation", "magofbeta", "isingbetac", "trg_svd", "svd", "svd_back", "fixedpoint", "StopFunction",
     "indexperm_symmetrize", "diaglocalhamiltonian", "tensorfromclassical", "getchi", "getD", "getd", "gets",
     "Context", "default_context", "DimensionMismatch", "TnadError", "magnetisation_value_and_grad", "dmag_tensor",
-    "dmodel_tensor", "trg_sweep",
+    "dmodel_tensor", "trg_sweep", "energy_and_gradient_fixedpoint",
 ]
 
 _default_ctx: Optional[Context] = None
@@ -372,6 +372,13 @@ def energy(h, ipeps, chi: int, tol: float, maxit: int, ctx=None) -> float:
 def energy_and_gradient(h, ipeps, chi: int, tol: float, maxit: int, ctx=None):
     """energy and `Zygote.gradient(x -> energy(h, x; ...), ipeps)[1].bulk` in one call (forward shared)."""
     return _ctx(ctx).energy(h, _bulk_of(ipeps), chi, tol, maxit, grad=True)
+
+
+def energy_and_gradient_fixedpoint(h, ipeps, chi: int, tol: float, maxit: int, bwd_tol: float = 1e-12, bwd_maxit: int = 500,
+                                   ctx=None):
+    """Opt-in: energy with the implicit fixed-point gradient (tnad_energy_fixedpoint); equals energy_and_gradient for a
+    converged CTMRG, needs one step record instead of a tape over all iterations."""
+    return _ctx(ctx).energy_fixedpoint(h, _bulk_of(ipeps), chi, tol, maxit, bwd_tol, bwd_maxit)
 
 
 def magnetisation(model: HamiltonianModel, beta: float, chi: int, rng=None, tol=1e-6, maxit=100, env="random",

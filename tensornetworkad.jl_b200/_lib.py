@@ -60,6 +60,8 @@ SIGNATURES = {
                                         C.c_void_p, C.c_int, c_double_p]),
     "tnad_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                               c_double_p, C.c_void_p, c_int_p]),
+    "tnad_energy_fixedpoint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                         C.c_double, C.c_int, c_double_p, C.c_void_p, c_int_p, c_int_p]),
     "tnad_magnetisation_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, c_double_p]),
     "tnad_last_timing": (C.c_int, [C.c_void_p, c_double_p]),
@@ -422,6 +424,18 @@ class Context:
                                         _p(g), C.byref(steps)))
         self.last_steps = steps.value
         return (e.value, g) if grad else e.value
+
+    def energy_fixedpoint(self, h, A, chi, tol, maxit, bwd_tol=1e-12, bwd_maxit=500):
+        """Energy and its implicit (fixed-point) gradient: (e, grad); self.last_steps / self.last_bwd_iters are set."""
+        h, A = farray(h), farray(A)
+        d, s = A.shape[0], A.shape[4]
+        e = C.c_double(0.0)
+        steps, it = C.c_int(0), C.c_int(0)
+        g = np.empty(A.shape, order="F")
+        self.check(self.lib.tnad_energy_fixedpoint(self.h, _p(h), _p(A), d, s, int(chi), float(tol), int(maxit), float(bwd_tol),
+                                                   int(bwd_maxit), C.byref(e), _p(g), C.byref(steps), C.byref(it)))
+        self.last_steps, self.last_bwd_iters = steps.value, it.value
+        return e.value, g
 
     def sytrd(self, a):
         """A = Q tridiag(d, e) Q' (stage of the direct eigensolver)."""

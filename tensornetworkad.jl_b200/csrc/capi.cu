@@ -654,6 +654,22 @@ int tnad_energy(tnad_ctx* c, const double* h, const double* A, int d, int s, int
   TNAD_API_END(c)
 }
 
+int tnad_energy_fixedpoint(tnad_ctx* c, const double* h, const double* A, int d, int s, int chi, double tol, int maxit,
+                           double bwd_tol, int bwd_maxit, double* e, double* gradA, int* steps_done, int* bwd_iters) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(e && d >= 1 && s >= 1, "tnad_energy_fixedpoint: bad arguments");
+  timing_begin(c);
+  Tens th = t_in(c, h, {s, s, s, s}), tA = t_in(c, A, {d, d, d, d, s});
+  Tens g;
+  {
+    Span sp(c, 0);
+    *e = energy_fixedpoint(c, th, tA, chi, tol, maxit, bwd_tol, bwd_maxit, gradA ? &g : nullptr, steps_done, bwd_iters);
+  }
+  if (gradA) t_out(c, g, gradA);
+  timing_end(c);
+  TNAD_API_END(c)
+}
+
 int tnad_magnetisation_readout(tnad_ctx* c, const double* a, const double* m, int D, const double* corner,
                                const double* edge, int chi, double* mag) {
   TNAD_API_BEGIN(c)

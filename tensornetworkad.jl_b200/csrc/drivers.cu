@@ -507,6 +507,87 @@ double energy(tnad_ctx* c, const Tens& h, const Tens& A, int chi, double tol, in
   return y;
 }
 
+// Implicit (fixed-point) gradient of the energy -- opt-in alternative to the unrolled reverse sweep (north_star item 3,
+// SURVEY 8f.2).  At a converged environment x* = f(x*, a) of the gauge-fixed step f (canonical column signs make the fixed
+// point elementwise), the cotangent of a is  J_a' (1 - J_x')^{-1} xbar  =  sum_k J_a' (J_x')^k xbar: the pullback of ONE
+// recorded step is applied repeatedly to the shrinking cotangent (Neumann series) until it has decayed by bwd_tol.  No
+// tape over the forward iterations: one step record instead of one per step.  Equal to the reference's gradient (which
+// back-propagates through every executed step with a constant initialisation, autodiff.jl:5) in the limit of a converged
+// CTMRG; it is NOT what the reference computes for short fixed-maxit runs.
+double energy_fixedpoint(tnad_ctx* c, const Tens& h, const Tens& A, int chi, double tol, int maxit, double bwd_tol,
+                         int bwd_maxit, Tens* gradA, int* steps, int* bwd_iters) {
+  TNAD_REQUIRE(A.rank == 5 && A.dim[0] == A.dim[1] && A.dim[1] == A.dim[2] && A.dim[2] == A.dim[3],
+               "size of tensor error, should be (d, d, d, d, s)");   // ipeps.jl:19-20
+  const int64_t s = A.dim[4];
+  TNAD_REQUIRE(h.rank == 4 && h.dim[0] == s && h.dim[1] == s && h.dim[2] == s && h.dim[3] == s, "energy: h must be (s,s,s,s)");
+  TNAD_REQUIRE(chi >= 1 && maxit >= 0 && bwd_maxit >= 1 && bwd_tol > 0.0, "energy_fixedpoint: bad arguments");
+  const double eta = 1e-40;
+  Tens xsum, As;
+  Tens ss_sym = t_alloc(c, {1});
+  ipeps_symmetrize(c, A, xsum, As, ss_sym.p);
+  Tens ap, a;
+  double_layer(c, As, ap, a);
+  const int64_t D = a.dim[0];
+  Tens corner = t_alloc(c, {(int64_t)chi, (int64_t)chi}), edge = t_alloc(c, {(int64_t)chi, D, (int64_t)chi});
+  init_raw(c, a, corner, edge);
+  std::vector<double> vals;
+  int nsteps = ctmrg_loop(c, a, corner, edge, tol, maxit, vals, nullptr);     // no tape
+  // one recorded step at the (converged) environment: its pullback is the linear map of the Neumann series
+  CtmrgStepRec rec;
+  Tens cn, en;
+  ctmrg_step(c, a, corner, edge, cn, en, vals, gradA ? &rec : nullptr);
+  ++nsteps;
+  if (steps) *steps = nsteps;
+  ExpvalTape et;
+  const double y = expectationvalue(c, h, ap, cn, en, gradA ? &et : nullptr);
+  if (bwd_iters) *bwd_iters = 0;
+  if (gradA) {
+    Span sp(c, 3);
+    // the implicit formula needs an ELEMENTWISE fixed point of the gauge-fixed step: f(x*) = x*.  With degenerate singular
+    // values at (or inside) the kept spectrum the eigenvectors of a multiplet rotate from step to step and only gauge
+    // invariants converge: refuse instead of returning a wrong gradient (the unrolled sweep handles that case).
+    {
+      Tens dc = t_clone(c, cn), de = t_clone(c, en);
+      tcopy(c, corner, dc, -1.0, 1.0);
+      tcopy(c, edge, de, -1.0, 1.0);
+      double* sq = c->scal + 56;
+      reduce(c, RED_SUMSQ, dc, nullptr, sq);
+      reduce(c, RED_SUMSQ, de, nullptr, sq + 1);
+      double v[2];
+      d2h(c, v, sq, 2);
+      const double res = std::sqrt(v[0] + v[1]);       // corner and edge have unit norm
+      if (!(res <= opt_d(c, "TNAD_FIXEDPOINT_RES", 1e-7)))
+        fail(TNAD_ERR_NOCONV, "energy_fixedpoint: the environment is not an elementwise fixed point of the step (|f(x) - x| = " +
+                                  std::to_string(res) + "): not converged, or degenerate singular values inside the kept spectrum; "
+                                  "use the unrolled gradient (tnad_energy)");
+    }
+    Tens apbar, cbar, ebar, Asbar;
+    expectationvalue_back(c, cn, en, et, 1.0, apbar, cbar, ebar);
+    Tens abar = t_alloc(c, {D, D, D, D}, true);
+    double* sq = c->scal + 52;
+    double nrm0 = 0.0;
+    int k = 0;
+    for (; k < bwd_maxit; ++k) {
+      reduce(c, RED_SUMSQ, cbar, nullptr, sq);
+      reduce(c, RED_SUMSQ, ebar, nullptr, sq + 1);
+      double v[2];
+      d2h(c, v, sq, 2);
+      const double nrm = std::sqrt(v[0] + v[1]);
+      TNAD_REQUIRE(std::isfinite(nrm), "energy_fixedpoint: the cotangent series diverged (is the environment converged?)");
+      if (k == 0) nrm0 = nrm;
+      if (nrm <= bwd_tol * nrm0) break;
+      Tens cb, eb;
+      ctmrg_step_backward(c, a, rec, cbar, ebar, abar, cb, eb, eta);   // abar += J_a' lambda_k; (cb, eb) = J_x' lambda_k
+      cbar = cb;
+      ebar = eb;
+    }
+    if (bwd_iters) *bwd_iters = k;
+    double_layer_back(c, As, apbar, abar, Asbar);
+    ipeps_symmetrize_back(c, Asbar, xsum, ss_sym.p, *gradA);
+  }
+  return y;
+}
+
 double magnetisation_readout(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge,
                              MagTape* tape) {
   // exampletensors.jl:63-68

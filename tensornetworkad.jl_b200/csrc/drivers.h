@@ -69,6 +69,8 @@ double expectationvalue(tnad_ctx* c, const Tens& h, const Tens& ap, const Tens& 
 void expectationvalue_back(tnad_ctx* c, const Tens& corner, const Tens& edge, const ExpvalTape& t, double ybar,
                            Tens& apbar, Tens& cornerbar, Tens& edgebar);
 double energy(tnad_ctx* c, const Tens& h, const Tens& A, int chi, double tol, int maxit, Tens* gradA, int* steps);
+double energy_fixedpoint(tnad_ctx* c, const Tens& h, const Tens& A, int chi, double tol, int maxit, double bwd_tol,
+                         int bwd_maxit, Tens* gradA, int* steps, int* bwd_iters);
 struct MagTape {
   Tens ct, ctc, e1, e2, env;
   double mag = 0.0, nrm = 1.0;

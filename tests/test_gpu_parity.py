@@ -868,3 +868,30 @@ def test_symeig_three_phase_matches_single_call(ctx, n):
     assert np.abs((u * s) @ v.T - m).max() <= 1e-12 * ref[0]
     u1, s1, v1 = ctx.svd_sym(m)
     assert np.abs(s - s1).max() <= 1e-13 * ref[0] and np.abs(u - u1).max() < 1e-9     # same canonical gauge
+
+
+@pytest.mark.gpu
+def test_fixedpoint_gradient_matches_unrolled_gradient_at_convergence(ctx):
+    """Opt-in implicit gradient (tnad_energy_fixedpoint): for a converged CTMRG it must agree with the unrolled reverse
+    sweep, i.e. with what the reference computes (test/variationalipeps.jl:121-134 runs tol=0, maxit=100)."""
+    h = T.hamiltonian(T.Heisenberg())
+    agreed = 0
+    for seed, chi in [(0, 8), (1, 8), (2, 10), (3, 12)]:
+        A = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(seed).standard_normal((2, 2, 2, 2, 2)))).bulk
+        e_u, g_u = T.energy_and_gradient(h, A, chi, 0.0, 150, ctx=ctx)
+        try:
+            e_f, g_f = T.energy_and_gradient_fixedpoint(h, A, chi, 0.0, 150, bwd_tol=1e-13, bwd_maxit=400, ctx=ctx)
+        except T.TnadError as ex:
+            # degenerate multiplet inside the kept spectrum: the environment converges only up to rotations and the
+            # library refuses the implicit formula (error 4) instead of returning a wrong gradient
+            assert ex.code == 4
+            continue
+        assert ctx.last_bwd_iters > 3
+        assert e_f == pytest.approx(e_u, rel=1e-10)
+        assert rel(g_f, g_u) < 1e-7
+        agreed += 1
+    assert agreed >= 1
+    A = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(0).standard_normal((2, 2, 2, 2, 2)))).bulk
+    eo, go = O.energy_value_and_grad(h, A, 8, 0.0, 150)
+    e_f, g_f = T.energy_and_gradient_fixedpoint(h, A, 8, 0.0, 150, bwd_tol=1e-13, bwd_maxit=400, ctx=ctx)
+    assert rel(g_f, go) < 1e-7 and e_f == pytest.approx(eo, rel=1e-10)
