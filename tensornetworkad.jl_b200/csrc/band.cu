@@ -498,49 +498,52 @@ __global__ void __launch_bounds__(Q2_NT, 1) k_q2_stage(const Q2Args a) {
   for (int k = 0; k < QH + UNR; ++k) x0[k] = x1[k] = 0.0;
   for (int i = tid; i < 2 * QS * QC; i += Q2_NT) (&xfer[0][0][0])[i] = 0.0;
 
-  auto stage_v = [&](int s, int buf) {   // cp.async the 32 x 32 reflector block of sweep s (nothing for sweeps without reflectors)
-    double* dst = vbuf[buf];
-    if (s >= 0 && s <= n - 3) {
-      const double* src = a.V2 + (long long)s * a.ldv + (long long)CB * a.q0;
-      const int avail = (int)min((long long)QS * CB, a.ldv - (long long)CB * a.q0);   // doubles available in this row
-      const int i = tid * 2;                       // 512 threads x 2 doubles = the whole block
-      if (i + 1 < avail) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + i));
-      } else {
-        dst[i] = i < avail ? src[i] : 0.0;
-        dst[i + 1] = 0.0;
-      }
-    }
-    if (tid < QS) {
-      const int qq = a.q0 + tid;
-      if (s >= 0 && s <= n - 3 && qq < a.NP) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(&tbuf[buf][tid]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(a.tau2 + (long long)s * a.NP + qq));
-      } else {
+  // Staging of sweep s: the 32 x 32 reflector block (16-byte cp.async per thread), the 32 taus, the 16 rows that enter the
+  // first slot.  Everything that does not depend on s is hoisted: per thread one source pointer per stream, moved by a
+  // constant per sweep.
+  const int v_avail = (int)min((long long)QS * CB, a.ldv - (long long)CB * a.q0);
+  const bool v_vec = 2 * tid + 1 < v_avail, v_one = 2 * tid < v_avail;
+  const double* v_src0 = a.V2 + (long long)CB * a.q0 + 2 * tid;                        // + s * ldv
+  const bool t_thr = tid < QS && a.q0 + tid < a.NP;
+  const double* t_src0 = a.tau2 + a.q0 + (tid < QS ? tid : 0);                          // + s * NP
+  const bool top_thr = tid >= 64 && tid < 64 + QC && blockIdx.x * QC + (tid - 64) < a.ncols;
+  const int top_c = tid - 64;
+  const double* top_src0 = a.sin ? a.sin + blockIdx.x * QC + top_c : a.X + 1 + (long long)(blockIdx.x * QC + top_c) * a.ldx;
+  const long long top_step = a.sin ? a.lds : 1;                                         // + s * top_step
+  const int top_smax = a.sin ? n - 2 : n - 2;                                           // row s + 1 <= n - 1 / stream rows 0 .. n-2
+  auto stage_v = [&](int s, int buf) {
+    if (s >= 0) {
+      if (s <= n - 3) {
+        double* dst = vbuf[buf] + 2 * tid;
+        const double* src = v_src0 + (long long)s * a.ldv;
+        if (v_vec) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src));
+        } else {
+          dst[0] = v_one ? src[0] : 0.0;
+          dst[1] = 0.0;
+        }
+        if (t_thr) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(&tbuf[buf][tid]);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(t_src0 + (long long)s * a.NP));
+        }
+      } else if (tid < QS) {
         tbuf[buf][tid] = 0.0;
       }
-    }
-    // the row that enters the first slot of the stage at sweep s (row s + 1 of the matrix for stage 0)
-    if (tid >= 64 && tid < 64 + QC) {
-      const int cc = tid - 64, col = blockIdx.x * QC + cc;
-      const double* src = nullptr;
-      if (s >= 0 && col < a.ncols) {
-        if (a.sin) {
-          if (s <= n - 2) src = a.sin + (long long)s * a.lds + col;
-        } else if (s + 1 < n) {
-          src = a.X + (s + 1) + (long long)col * a.ldx;
+      if (top_thr) {
+        if (s <= top_smax) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(&topbuf[buf][top_c]);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(top_src0 + (long long)s * top_step));
+        } else {
+          topbuf[buf][top_c] = 0.0;
         }
-      }
-      if (src) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(&topbuf[buf][cc]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
-      } else {
-        topbuf[buf][cc] = 0.0;
       }
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
+  for (int i = tid; i < NB * QS; i += Q2_NT) (&tbuf[0][0])[i] = 0.0;       // slots beyond NP keep tau = 0
+  for (int i = tid; i < NB * QC; i += Q2_NT) (&topbuf[0][0])[i] = 0.0;     // columns beyond ncols stay 0
+  __syncthreads();
 
 #pragma unroll
   for (int i = 0; i < NB - 1; ++i) stage_v(a.s_top - i, i);
