@@ -102,24 +102,43 @@ __device__ __forceinline__ bool mb_recv(unsigned long long* box, unsigned seq, d
 }
 
 // Householder reflector of the vector whose element `lane` is x (dlarfg): returns v_lane; tau, beta through references.
+// 1 / sqrt(x) and 1 / x for normal positive x without the library's special-case paths: hardware seed (MUFU.RSQ64H /
+// MUFU.RCP64H, about 20 bits) + Newton steps; the reflector scalars sit on the critical path of the chase pipeline
+__device__ __forceinline__ double fast_rsqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double fast_rcp_pos(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = y * fma(-x, y, 2.0);
+  y = y * fma(-x, y, 2.0);
+  y = y * fma(-x, y, 2.0);
+  return y;
+}
+
 __device__ __forceinline__ double warp_house(double x, int lane, double& tau, double& beta) {
   const double xn2 = wsum(lane >= 1 ? x * x : 0.0);
   const double alpha = __shfl_sync(0xffffffffu, x, 0);
-  if (xn2 == 0.0) {
+  const double s2 = fma(alpha, alpha, xn2);
+  if (xn2 == 0.0 || !(s2 > 1e-290 && s2 < 1e290)) {          // nothing to annihilate (or a degenerate scale): H = I
     tau = 0.0;
     beta = alpha;
     return lane == 0 ? 1.0 : 0.0;
   }
-  // one reciprocal square root and one reciprocal instead of a square root and two divisions (all three are software
-  // sequences on the critical path of the pipeline): beta = -sign(alpha) |x|, tau = (beta - alpha) / beta = 1 + |alpha| / |x|,
-  // v = x / (alpha - beta) = sign(alpha) x / (|alpha| + |x|)
-  const double s2 = fma(alpha, alpha, xn2);
-  const double rn = rsqrt(s2);
+  // one reciprocal square root and one reciprocal instead of a square root and two divisions:
+  // beta = -sign(alpha) |x|, tau = (beta - alpha) / beta = 1 + |alpha| / |x|, v = x / (alpha - beta) = sign(alpha) x / (|alpha| + |x|)
+  const double rn = fast_rsqrt_pos(s2);
   const double nrm = s2 * rn;
   const double aa = fabs(alpha);
   beta = alpha >= 0.0 ? -nrm : nrm;
   tau = fma(aa, rn, 1.0);
-  const double rc = 1.0 / (aa + nrm);
+  const double rc = fast_rcp_pos(aa + nrm);
   const double scale = alpha >= 0.0 ? rc : -rc;
   return lane == 0 ? 1.0 : x * scale;
 }
@@ -145,7 +164,7 @@ struct ChaseArgs {
 //   vbox (reflector from position t-1), rbox[2] (row from position t+1, double buffered by sweep parity: the D warp may
 //   lag the E warp by one hop), dbox (reflector E warp -> D warp), and a word the D warp uses to publish its progress
 constexpr int POS_BOXES = 4 * MB_WORDS + 2;
-constexpr int POS_DOUBLES = (2 + CB * WLD) + CB * WLD + 7 * 34 + POS_BOXES;
+constexpr int POS_DOUBLES = (2 + CB * WLD) + CB * WLD + CB * WLD + 7 * 34 + POS_BOXES;   // Ew, Dw, transpose scratch, vectors, boxes
 constexpr int BOXOFF = POS_DOUBLES - POS_BOXES;      // offset of a position's boxes inside its shared-memory slice
 
 // the E warp needs double 0 of the row message only, the D warp doubles 1 .. 32 (lane l <-> double 1 + l)
@@ -206,7 +225,8 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
   double* base = sm + (size_t)pw * POS_DOUBLES;
   double* Ew = base + 1;                       // one double of head room: the shifted store of row 1 touches Ew[-1]
   double* Dw = base + 2 + CB * WLD;
-  double* sv = Dw + CB * WLD;                  // own reflector, E warp's copy (34)
+  double* Tw = Dw + CB * WLD;                  // 32 x 33 scratch of the E warp (column sums by transposition)
+  double* sv = Tw + CB * WLD;                  // own reflector, E warp's copy (34)
   double* svp = sv + 34;                       // previous reflector of the sweep + tau (34)
   double* sw = svp + 34;                       // E-phase coefficients w_k (34)
   double* stop = sw + 34;                      // leaving top row, E part (34)
@@ -286,6 +306,8 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
       CH_TICK(0)
       double v, tau, beta;
       double Er[CB];
+      double e0 = 0.0;                           // row 0 of the block after the right-apply, column `lane`
+      double fr = 0.0;                           // coefficient of my row in the right-apply
       if (t == 0) {
         double x = Ew[lane * WLD + (CB - 1)];
         if (s > 0 && lane == CB - 1) x = ent;
@@ -299,66 +321,76 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
           for (int k = 0; k < CB - 1; ++k) Er[k] = 0.0;
           Er[CB - 1] = ent;
         }
+        const double e0k = Ew[lane];               // row 0 of the block seen by columns: the row that will leave
         CH_TICK(2)
         if (!mb_recv(my_vbox, seq, svp, lane, a.err)) break;
         CH_TICK(1)
-        {
-          const double taup = svp[CB];
-          double dot0 = 0.0, dot1 = 0.0, dot2 = 0.0, dot3 = 0.0;
+        e0 = e0k;
+        const double taup = svp[CB];
+        double dot0 = 0.0, dot1 = 0.0, dot2 = 0.0, dot3 = 0.0;
 #pragma unroll
-          for (int k = 0; k < CB; k += 4) {
-            dot0 = fma(Er[k], svp[k], dot0);
-            dot1 = fma(Er[k + 1], svp[k + 1], dot1);
-            dot2 = fma(Er[k + 2], svp[k + 2], dot2);
-            dot3 = fma(Er[k + 3], svp[k + 3], dot3);
-          }
-          const double f = taup * ((dot0 + dot1) + (dot2 + dot3));
-#pragma unroll
-          for (int k = 0; k < CB; ++k) Er[k] = fma(-f, svp[k], Er[k]);
+        for (int k = 0; k < CB; k += 4) {
+          dot0 = fma(Er[k], svp[k], dot0);
+          dot1 = fma(Er[k + 1], svp[k + 1], dot1);
+          dot2 = fma(Er[k + 2], svp[k + 2], dot2);
+          dot3 = fma(Er[k + 3], svp[k + 3], dot3);
         }
+        fr = taup * ((dot0 + dot1) + (dot2 + dot3));
+        Er[0] = fma(-fr, svp[0], Er[0]);           // only column 0 of the right-apply sits in front of the reflector
         v = warp_house(Er[0], lane, tau, beta);
+        // beta is E'[31][31] of position t-1's next sweep -- all its E warp needs of the leaving row: send it before the
+        // column sums (the loop t -> t+1 -> t closes here: dot, reflector, two links)
+        if (lane == 0) mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, 0, beta);
       }
       // reflector out at once: to my D warp and to position t+1
-      mb_send(dbox, seq, lane, v);
-      if (lane == 0) mb_send(dbox, seq, CB, tau);
       if (s < nx_sweeps) {
         mb_send(nx_vbox, seq, lane, v);
         if (lane == 0) mb_send(nx_vbox, seq, CB, tau);
       }
+      mb_send(dbox, seq, lane, v);
+      if (lane == 0) mb_send(dbox, seq, CB, tau);
+      if (t > 0) {                                 // the rest of the right-apply
+#pragma unroll
+        for (int k = 1; k < CB; ++k) Er[k] = fma(-fr, svp[k], Er[k]);
+        e0 = fma(-__shfl_sync(0xffffffffu, fr, 0), svp[lane], e0);     // row 0 after the right-apply, one column per lane
+      }
+      double wl = 0.0;
       if (t > 0) {
-        double val[CB];
+        // column sums c_k = sum_r v_r E[r][k]: every lane stores its weighted row, lane k adds up column k (a transposition
+        // through shared memory: 80 instructions instead of the 217 of a recursive-halving shuffle tree -- the warp is
+        // alone on its scheduler, so the instruction count is the latency)
 #pragma unroll
-        for (int k = 0; k < CB; ++k) val[k] = v * Er[k];
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          const bool up = (lane & o) != 0;
-#pragma unroll
-          for (int k = 0; k < o; ++k) {
-            const double snd = up ? val[k] : val[k + o];
-            const double keep = up ? val[k + o] : val[k];
-            val[k] = keep + __shfl_xor_sync(0xffffffffu, snd, o);
-          }
-        }
-        sw[lane] = lane == 0 ? 0.0 : tau * val[0];
+        for (int k = 0; k < CB; ++k) Tw[lane * WLD + k] = v * Er[k];
         __syncwarp();
-        // left-apply and store the block of the next sweep shifted by (1,1); row 0 (v_0 = 1) is the E part of the row
-        // that leaves to position t-1: lane 0 stores it to the send buffer with the same instructions
-        {
-          double wk[CB];                             // all loads first: the stores below may alias sw for the compiler
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
-          for (int k = 1; k < CB; ++k) wk[k] = sw[k];
-          double* dst = lane == 0 ? stop : Ew + (lane - 1) * WLD - 1;
-#pragma unroll
-          for (int k = 1; k < CB; ++k) dst[k] = fma(-v, wk[k], Er[k]);     // column 0 is annihilated: not stored
-          if (lane == 0) stop[0] = beta;
+        for (int r = 0; r < CB; r += 4) {
+          c0 += Tw[r * WLD + lane];
+          c1 += Tw[(r + 1) * WLD + lane];
+          c2 += Tw[(r + 2) * WLD + lane];
+          c3 += Tw[(r + 3) * WLD + lane];
         }
-        __syncwarp();
+        wl = lane == 0 ? 0.0 : tau * ((c0 + c1) + (c2 + c3));
+        // the E part of the row that leaves to position t-1 (v_0 = 1): E[0][k] - w_k, straight from lane k
         CH_TICK(2)
-        mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, lane, stop[lane]);
+        if (lane >= 1) mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, lane, e0 - wl);
         CH_TICK(4)
       }
+      // off the critical path: reflector store, left-apply, shifted block of the next sweep
       a.V2[(long long)s * a.ldv + CB * t + lane] = v;
       if (lane == 0) a.tau2[(long long)s * a.NP + t] = tau;
+      if (t > 0) {
+        sw[lane] = wl;
+        __syncwarp();
+        double wk[CB];                             // all loads first: the stores below may alias sw for the compiler
+#pragma unroll
+        for (int k = 1; k < CB; ++k) wk[k] = sw[k];
+        if (lane >= 1) {
+          double* dst = Ew + (lane - 1) * WLD - 1;
+#pragma unroll
+          for (int k = 1; k < CB; ++k) dst[k] = fma(-v, wk[k], Er[k]);     // column 0 is annihilated: not stored
+        }
+      }
       __syncwarp();
       CH_TICK(3)
     }
