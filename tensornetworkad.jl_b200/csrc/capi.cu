@@ -116,6 +116,7 @@ int tnad_destroy(tnad_ctx* c) {
   if (c->tstart) cudaEventDestroy(c->tstart);
   if (c->tstop) cudaEventDestroy(c->tstop);
   cudaFree(c->scal);
+  if (c->gemm_cnt) cudaFree(c->gemm_cnt);
   cudaFree(c->partial);
   cudaFreeHost(c->hpin);
   tnad::symeig_cache_free(c);
@@ -214,7 +215,8 @@ int tnad_contract(tnad_ctx* c, const char* spec, const double* A, const int64_t*
   Tens tC;
   if (beta != 0.0) tC = t_in(c, C, dc);
   else tC = (c->pointer_mode == TNAD_POINTER_DEVICE) ? t_wrap(C, dc) : t_alloc_v(c, dc);
-  contract(c, spec, tA, tB, tC, alpha, beta);
+  const int reps = beta == 0.0 ? std::max(1, opt_i(c, "TNAD_CONTRACT_REPS", 1)) : 1;   // measurement aid: the same product enqueued reps times
+  for (int r = 0; r < reps; ++r) contract(c, spec, tA, tB, tC, alpha, beta);
   if (c->pointer_mode == TNAD_POINTER_DEVICE) sync(c);
   else t_out(c, tC, C);
   TNAD_API_END(c)

@@ -87,6 +87,8 @@ struct tnad_ctx {
   double* hpin = nullptr;      // pinned host staging (HPIN_SLOTS doubles)
   int num_sms = 148;
   int coop_launch = 0;         // cudaDevAttrCooperativeLaunch, queried once at tnad_create
+  int* gemm_cnt = nullptr;     // split-K tile counters of the TMA GEMM kernel (zero between launches)
+  int64_t gemm_tma_n = 0, gemm_fallback_n = 0;   // products on the TMA kernel / on the cp.async kernel
   // A/B switches: every TNAD_* environment variable is read ONCE at tnad_create into this table; tnad_set_option
   // changes an entry afterwards.  Nothing on the hot path calls getenv.
   std::map<std::string, std::string> opts;
@@ -214,6 +216,7 @@ struct GemmDesc {
   double* ws;
 };
 void gemm_run(tnad_ctx* c, const GemmDesc& d);
+bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d);   // gemm_tma.cu: false = operands not expressible as tensor maps
 
 // einsum pairwise contraction C[..] = alpha * sum A[..] B[..] + beta C[..]
 GemmDesc contract_plan(const char* spec, const Tens& A, const Tens& B, const Tens& C);

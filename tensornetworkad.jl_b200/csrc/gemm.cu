@@ -354,6 +354,13 @@ void launch_layout(tnad_ctx* c, const GemmDesc& d) {
 
 void gemm_run(tnad_ctx* c, const GemmDesc& d0) {
   if (d0.M <= 0 || d0.N <= 0 || d0.batch <= 0) return;
+  if (gemm_tma_try(c, d0)) {
+    c->gemm_tma_n++;
+    return;
+  }
+  c->gemm_fallback_n++;
+  if (opt_i(c, "TNAD_GEMM_DEBUG", 0))
+    fprintf(stderr, "[tnad gemm] cp.async kernel for M=%d N=%d K=%d batch=%d (akf %d bkf %d)\n", d0.M, d0.N, d0.K, d0.batch, d0.a_kfast, d0.b_kfast);
   GemmDesc d = d0;
   bool large = d.M >= 96 && d.N >= 96;
   {
