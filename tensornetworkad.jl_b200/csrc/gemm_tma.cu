@@ -147,6 +147,7 @@ __device__ __forceinline__ Unit unit_of(const TmaGemm& g, int u) {
 // producer warp.  CTA b works on the units b, b + G, b + 2G, ... (G = grid size); group 0 takes the even ones of that
 // list, group 1 the odd ones, and group 1 starts half a tile late, so that the epilogue (global stores) of one group
 // runs under the main loop of the other and the FP64 tensor pipe always has a main loop to serve.
+template <bool AKF, bool BKF>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ TmaGemm g) {
@@ -260,27 +261,33 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int gq = lane >> 2, t = lane & 3;
   const int wm0 = (cw & 1) * 32, wn0 = (cw >> 1) * 32;
   const unsigned char* ringg = sgen + grp * NSTAGE * 2 * TILE_BYTES;
-  // byte offset of element (row, k) inside a tile = rp[row block] + kp[kk] (both layouts separate this way)
-  int arp[4], akp[4], brp[4], bkp[4];
+  // Fragment addressing.  Lane (gq, t) feeds DMMA step kk with k = 8 (kk / 2) + 4 (t / 2) + 2 (t % 2) + kk % 2, and the
+  // eight rows of a fragment block are assigned to the lanes so that ONE 16-byte load brings two fragments and the eight
+  // lanes of every quarter warp hit eight different 16-byte chunks (the swizzle is chunk ^= line % 8):
+  //   k-fast tile  [row][16 k]:        row(blk, gq) = 8 blk + 4 (gq % 2) + gq / 2; the load at chunk (4 p + t) ^ (row % 8) of
+  //                                    the row holds k-steps 2p and 2p + 1 of that row
+  //   row-fast tile [row / 16][k][16]: row(blk, gq) = 16 (blk / 2) + 2 gq + blk % 2; the load at chunk gq ^ (k % 8) of line
+  //                                    (row / 16) * 16 + k holds the rows of blocks 2q and 2q + 1
+  // (64-bit shared loads are served per half warp, 128-bit loads per quarter warp: the round-2 layout that was
+  // conflict-free over a full warp needed 4 wavefronts per LDS.64, ncu l1tex__data_bank_conflicts = 2 per load.)
+  int offa[8], offb[8];
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int kk = x;
-    const int k7 = 4 * (t >> 1) + 2 * (kk & 1) + (t & 1);          // k mod 8 of this lane in step kk
-    const int kfull = 8 * (kk >> 1) + k7;
-    // k-fast layout: row * 128 + (((k >> 1) ^ (row & 7)) << 4) + ((k & 1) << 3), row & 7 == gq
-    const int kp_kf = (((kfull >> 1) ^ gq) << 4);
-    // row-fast layout: ((row >> 4) * 16 + k) * 128 + ((((row & 15) >> 1) ^ (k & 7)) << 4) + ((row & 1) << 3)
-    const int kp_rf = kfull * 128 + ((((gq >> 1) ^ (k7 & 3))) << 4);
-    akp[x] = g.a.kfast ? kp_kf : kp_rf;
-    bkp[x] = g.b.kfast ? kp_kf : kp_rf;
-    const int i = x;
-    const int ra = wm0 + 8 * i + gq, rb = wn0 + 8 * i + gq;
-    const int rp_kf_a = ra * 128 + ((t & 1) << 3), rp_kf_b = rb * 128 + ((t & 1) << 3);
-    const int hi4 = ((4 * (i & 1)) ^ (4 * (t >> 1))) << 4;
-    const int rp_rf_a = (ra >> 4) * 2048 + hi4 + ((gq & 1) << 3), rp_rf_b = (rb >> 4) * 2048 + hi4 + ((gq & 1) << 3);
-    arp[x] = g.a.kfast ? rp_kf_a : rp_rf_a;
-    brp[x] = g.b.kfast ? rp_kf_b : rp_rf_b;
+  for (int x = 0; x < 8; ++x) {
+    {
+      const int blk = x >> 1, p = x & 1;                         // k-fast: (row block, pair of k-steps)
+      const int ra = wm0 + 8 * blk + 4 * (gq & 1) + (gq >> 1), rb = wn0 + 8 * blk + 4 * (gq & 1) + (gq >> 1);
+      const int ka = ra * 128 + (((4 * p + t) ^ (ra & 7)) << 4), kb = rb * 128 + (((4 * p + t) ^ (rb & 7)) << 4);
+      const int q = x >> 2, kk = x & 3;                          // row-fast: (pair of row blocks, k-step)
+      const int k = 8 * (kk >> 1) + 4 * (t >> 1) + 2 * (t & 1) + (kk & 1);
+      const int ma = (((wm0 >> 4) + q) * 16 + k) * 128 + ((gq ^ (k & 7)) << 4);
+      const int mb = (((wn0 >> 4) + q) * 16 + k) * 128 + ((gq ^ (k & 7)) << 4);
+      offa[x] = AKF ? ka : ma;
+      offb[x] = BKF ? kb : mb;
+    }
   }
+  // tile-local row of (block i, lane group gq) / column of (block j, c = 2 t + e)
+  auto rowmap = [&](int i, int gg) { return AKF ? wm0 + 8 * i + 4 * (gg & 1) + (gg >> 1) : wm0 + 16 * (i >> 1) + 2 * gg + (i & 1); };
+  auto colmap = [&](int j, int cc) { return BKF ? wn0 + 8 * j + 4 * (cc & 1) + (cc >> 1) : wn0 + 16 * (j >> 1) + 2 * cc + (j & 1); };
   const double alpha = g.alpha, beta = g.beta;
   int it = 0;
   bool first = true;
@@ -297,24 +304,54 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       if (!mbar_wait(full0 + 8 * s, (unsigned)((it / NSTAGE) & 1))) __trap();
       const unsigned char* as = ringg + s * 2 * TILE_BYTES;
       const unsigned char* bs = as + TILE_BYTES;
-      double af[2][4], bf[2][4];
+      // half p of the stage = k-steps 2p, 2p + 1: fragments f[half][block][step]
+      double af[2][4][2], bf[2][4][2];
+      auto load_half = [&](int p, double (&fa)[4][2], double (&fb)[4][2]) {
+        if (AKF) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[0][i] = *reinterpret_cast<const double*>(as + arp[i] + akp[0]);
+          for (int i = 0; i < 4; ++i) {
+            const double2 v = *reinterpret_cast<const double2*>(as + offa[2 * i + p]);
+            fa[i][0] = v.x;
+            fa[i][1] = v.y;
+          }
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[0][j] = *reinterpret_cast<const double*>(bs + brp[j] + bkp[0]);
+          for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (kk < 3) {                                // fragments of the next step are in flight under this step's DMMAs
-#pragma unroll
-          for (int i = 0; i < 4; ++i) af[(kk + 1) & 1][i] = *reinterpret_cast<const double*>(as + arp[i] + akp[kk + 1]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bf[(kk + 1) & 1][j] = *reinterpret_cast<const double*>(bs + brp[j] + bkp[kk + 1]);
+            for (int h = 0; h < 2; ++h) {
+              const double2 v = *reinterpret_cast<const double2*>(as + offa[4 * q + 2 * p + h]);
+              fa[2 * q][h] = v.x;
+              fa[2 * q + 1][h] = v.y;
+            }
         }
+        if (BKF) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+          for (int j = 0; j < 4; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(bs + offb[2 * j + p]);
+            fb[j][0] = v.x;
+            fb[j][1] = v.y;
+          }
+        } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[kk & 1][i], bf[kk & 1][j]);
-      }
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double2 v = *reinterpret_cast<const double2*>(bs + offb[4 * q + 2 * p + h]);
+              fb[2 * q][h] = v.x;
+              fb[2 * q + 1][h] = v.y;
+            }
+        }
+      };
+      load_half(0, af[0], bf[0]);
+      load_half(1, af[1], bf[1]);                  // in flight under the 32 DMMAs of the first half
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[p][i][h], bf[p][j][h]);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(empty0 + 8 * s);
@@ -324,7 +361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     first = false;
 
     // ------------------------------------------------ epilogue ------------------------------------------------
-    // thread holds C[m = m0 + wm0 + 8 i + gq][n = n0 + wn0 + 8 j + 2 t + {0, 1}]
+    // thread holds C[m0 + rowmap(i, gq)][n0 + colmap(j, 2 t + {0, 1})]
     if (S > 1) {
       // partial tile -> workspace [tile][split][64 x 64, m fastest]; the last arriver sums in split order
       double* wt = g.ws + (long long)un.tile * S * (TM * TN);
@@ -334,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) __stcg(w + (wm0 + 8 * i + gq) + TM * (wn0 + 8 * j + 2 * t + e), acc[i][j][e]);
+          for (int e = 0; e < 2; ++e) __stcg(w + rowmap(i, gq) + TM * colmap(j, 2 * t + e), acc[i][j][e]);
       __threadfence();
       asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(32 * NCONS) : "memory");
       if (cw == 0 && lane == 0) {
@@ -362,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int off = (wm0 + 8 * i + gq) + TM * (wn0 + 8 * j + 2 * t + e);
+              const int off = rowmap(i, gq) + TM * colmap(j, 2 * t + e);
               v0[j][e] = __ldcg(w2 + off);
               v1[j][e] = two ? __ldcg(w2 + TM * TN + off) : 0.0;
             }
@@ -393,10 +430,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) coff[j][e] = s_off[grp][TM + wn0 + j * 8 + 2 * t + e];
+      for (int e = 0; e < 2; ++e) coff[j][e] = s_off[grp][TM + colmap(j, 2 * t + e)];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long ro = s_off[grp][wm0 + i * 8 + gq];
+      const long long ro = s_off[grp][rowmap(i, gq)];
       if (ro >= 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -573,14 +610,18 @@ bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d) {
   g.units = (int)(tiles * S);
   g.dbg_nofetch = opt_i(c, "TNAD_GEMM_NOFETCH", 0);
   const size_t smem = (size_t)NGRP * NSTAGE * 2 * TILE_BYTES + (NGRP * 2 * NSTAGE + 1) * 8 + 1024;
-  static std::atomic<unsigned long long> attr_devs{0};
-  if (!((attr_devs.load(std::memory_order_acquire) >> (c->device & 63)) & 1ULL)) {
-    TNAD_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_devs.fetch_or(1ULL << (c->device & 63), std::memory_order_release);
+  void (*kern)(CUtensorMap, CUtensorMap, TmaGemm) =
+      g.a.kfast ? (g.b.kfast ? gemm_tma_kernel<true, true> : gemm_tma_kernel<true, false>)
+                : (g.b.kfast ? gemm_tma_kernel<false, true> : gemm_tma_kernel<false, false>);
+  const int variant = (g.a.kfast ? 2 : 0) + (g.b.kfast ? 1 : 0);
+  static std::atomic<unsigned long long> attr_devs[4];
+  if (!((attr_devs[variant].load(std::memory_order_acquire) >> (c->device & 63)) & 1ULL)) {
+    TNAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_devs[variant].fetch_or(1ULL << (c->device & 63), std::memory_order_release);
   }
   const int grid = (int)std::min<long long>(c->num_sms, g.units);
   KTimer kt(c, KF_GEMM);
-  gemm_tma_kernel<<<grid, NTHREADS, smem, c->stream>>>(mapA, mapB, g);
+  kern<<<grid, NTHREADS, smem, c->stream>>>(mapA, mapB, g);
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
   return true;
