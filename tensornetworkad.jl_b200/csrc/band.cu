@@ -17,6 +17,7 @@
 //
 // tools/twostage_proto.py states the same data flow in NumPy (sb2st_systolic, apply_q2_systolic) and is tested on the CPU.
 #include "eigdc.h"
+#include <functional>
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <chrono>
@@ -1481,7 +1482,8 @@ int64_t chase_positions(int64_t n) { return n >= 2 ? (n - 2) / CB + 1 : 1; }
 
 // Band (lower storage AB, ldab >= 33, half bandwidth 32) -> tridiagonal (dd, ee); reflectors to V2 ((n-2) x ldv with
 // ldv = 32 * chase_positions(n), zero-initialised by the caller) and tau2 ((n-2) x NP, zero-initialised).
-void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, double* ee, double* V2, int64_t ldv, double* tau2) {
+void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, double* ee, double* V2, int64_t ldv, double* tau2,
+           const std::function<void(int)>& overlap) {
   TNAD_REQUIRE(n >= 3 && ldab >= CB + 1, "sb2st: need n >= 3 and a band store with 33 rows");
   TNAD_REQUIRE(c->coop_launch, "sb2st: the chase kernel needs cooperative (co-resident) launches");
   const int NP = (int)chase_positions(n);
@@ -1533,6 +1535,9 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
     TNAD_CUDA(le);
   }
   c->launches++;
+  // the chase owns Gp SMs for milliseconds and leaves the rest of the device idle: the caller may enqueue independent
+  // work on another stream here, before the host waits for the pipeline's status word
+  if (overlap) overlap(Gp);
   int herr = 0;
   TNAD_CUDA(cudaMemcpyAsync(&herr, a.err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   sync(c);

@@ -116,7 +116,8 @@ int tnad_destroy(tnad_ctx* c) {
   if (c->tstart) cudaEventDestroy(c->tstart);
   if (c->tstop) cudaEventDestroy(c->tstop);
   cudaFree(c->scal);
-  if (c->gemm_cnt) cudaFree(c->gemm_cnt);
+  for (int* p : c->gemm_cnt)
+    if (p) cudaFree(p);
   cudaFree(c->partial);
   cudaFreeHost(c->hpin);
   tnad::symeig_cache_free(c);

@@ -149,13 +149,19 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   long long* kofB = kofA + STAGES * BK;        // [STAGES][BK]
 
   const int tid = threadIdx.x;
+  // The level sets are read through out-of-line calls (code size); a reference into the kernel parameters turns every
+  // access into a generic load with hundreds of cycles of latency (ncu: long-scoreboard stalls, about 0.5 us per call,
+  // 12 calls per thread in the epilogue -- most of the 13 us a tiny product took).  A copy in shared memory costs 30 cycles.
+  __shared__ LvlSet slv[9];                      // am, ak, bk, bn, cm, cn, ab, bb, cb (their order in GemmDesc)
+  if (tid < 9) slv[tid] = (&d.am)[tid];
+  __syncthreads();
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int S = d.splitk > 1 ? d.splitk : 1;
   const int bz = blockIdx.z / S, sp = blockIdx.z - bz * S;
 
-  const double* gA = d.A + lvl_off_ni(d.ab, bz);
-  const double* gB = d.B + lvl_off_ni(d.bb, bz);
+  const double* gA = d.A + lvl_off_ni(slv[6], bz);
+  const double* gB = d.B + lvl_off_ni(slv[7], bz);
 
   // this CTA's K range (whole k-tiles)
   const int K = d.K;
@@ -165,13 +171,13 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   const int nkt = max(0, min(per, nkt_all - kt0));
   const int kbase = kt0 * BK;
 
-  for (int r = tid; r < BM; r += NT) rowA[r] = (m0 + r < d.M) ? lvl_off_ni(d.am, m0 + r) : -1;
-  for (int r = tid; r < BN; r += NT) rowB[r] = (n0 + r < d.N) ? lvl_off_ni(d.bn, n0 + r) : -1;
+  for (int r = tid; r < BM; r += NT) rowA[r] = (m0 + r < d.M) ? lvl_off_ni(slv[0], m0 + r) : -1;
+  for (int r = tid; r < BN; r += NT) rowB[r] = (n0 + r < d.N) ? lvl_off_ni(slv[3], n0 + r) : -1;
   // k-offset tables of the first STAGES tiles
   for (int q = tid; q < 2 * STAGES * BK; q += NT) {
     const int which = q / (STAGES * BK), rem = q % (STAGES * BK);
     const int k = kbase + rem;                                   // tile (rem / BK) sits in slot (rem / BK)
-    const long long o = (rem / BK < nkt && k < K) ? lvl_off_ni(which ? d.bk : d.ak, k) : -1;
+    const long long o = (rem / BK < nkt && k < K) ? lvl_off_ni(slv[which ? 2 : 1], k) : -1;
     (which ? kofB : kofA)[rem] = o;
   }
   __syncthreads();
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
       if (tid < 2 * BK && fk < nkt) {
         const int which = tid / BK, kl = tid % BK;
         const int k = kbase + fk * BK + kl;
-        (which ? kofB : kofA)[(fk % STAGES) * BK + kl] = k < K ? lvl_off_ni(which ? d.bk : d.ak, k) : -1;
+        (which ? kofB : kofA)[(fk % STAGES) * BK + kl] = k < K ? lvl_off_ni(slv[which ? 2 : 1], k) : -1;
       }
     }
     const double* as = As + (kt % STAGES) * A_ELEMS;
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
     }
     return;
   }
-  double* gC = d.C + lvl_off_ni(d.cb, bz);
+  double* gC = d.C + lvl_off_ni(slv[8], bz);
   const double alpha = d.alpha, beta = d.beta;
   long long coff[TN][2];
   bool cok[TN][2];
@@ -271,13 +277,13 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
     for (int e = 0; e < 2; ++e) {
       const int n = n0 + wn0 + j * 8 + 2 * t + e;
       cok[j][e] = n < d.N;
-      coff[j][e] = cok[j][e] ? lvl_off_ni(d.cn, n) : 0;
+      coff[j][e] = cok[j][e] ? lvl_off_ni(slv[5], n) : 0;
     }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + wm0 + i * 8 + g;
     if (m < d.M) {
-      const long long ro = lvl_off_ni(d.cm, m);
+      const long long ro = lvl_off_ni(slv[4], m);
 #pragma unroll
       for (int j = 0; j < TN; ++j)
 #pragma unroll

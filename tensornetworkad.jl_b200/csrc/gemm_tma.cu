@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // programmatic dependent launch: the grid is launched while its predecessor in the stream drains (the launch latency
+  // and the set-up above overlap that tail); nothing before this point touches global memory
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const bool producer = warp >= NGRP * NCONS;
   const int grp = producer ? warp - NGRP * NCONS : warp / NCONS;
@@ -596,13 +600,14 @@ bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d) {
   if (tiles * S > 0x7fffffffLL) return false;
   Tens ws;
   if (S > 1) {
-    if (!c->gemm_cnt) {
-      TNAD_CUDA(cudaMalloc((void**)&c->gemm_cnt, CNT_SLOTS * sizeof(int)));
-      TNAD_CUDA(cudaMemsetAsync(c->gemm_cnt, 0, CNT_SLOTS * sizeof(int), c->stream));
+    int*& cnt = c->gemm_cnt[c->stream == c->stream2 ? 1 : 0];   // concurrent products on the two streams must not share counters
+    if (!cnt) {
+      TNAD_CUDA(cudaMalloc((void**)&cnt, CNT_SLOTS * sizeof(int)));
+      TNAD_CUDA(cudaMemsetAsync(cnt, 0, CNT_SLOTS * sizeof(int), c->stream));
     }
     ws = t_alloc(c, {(int64_t)tiles * S * TM * TN});
     g.ws = ws.p;
-    g.cnt = c->gemm_cnt;
+    g.cnt = cnt;
   }
   g.splitk = S;
   g.tm = (int)tm;
@@ -619,9 +624,19 @@ bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d) {
     TNAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_devs[variant].fetch_or(1ULL << (c->device & 63), std::memory_order_release);
   }
-  const int grid = (int)std::min<long long>(c->num_sms, g.units);
+  const int grid = (int)std::min<long long>(c->gemm_grid_cap > 0 ? std::min(c->gemm_grid_cap, c->num_sms) : c->num_sms, g.units);
   KTimer kt(c, KF_GEMM);
-  kern<<<grid, NTHREADS, smem, c->stream>>>(mapA, mapB, g);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = opt_i(c, "TNAD_GEMM_PDL", 1) ? 1 : 0;
+  TNAD_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, g));
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
   return true;

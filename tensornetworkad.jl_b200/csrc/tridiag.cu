@@ -1018,31 +1018,40 @@ __global__ void k_load_symm(double* dst, long long ldd, const double* __restrict
 }
 
 // Compact WY factor of one panel (dlarft, forward / columnwise): T upper triangular, H_0..H_{k-1} = I - V T V'.
-// G = V'V (k x k, ldg), one CTA.
+// G = V'V (k x k, ldg), one CTA per panel, thread t owns ROW t of T: T[t][c] = -tau_c sum_{t <= q < c} T[t][q] G[q][c] only
+// involves the thread's own row, so the recurrence needs no barrier and no exchange (the column-oriented form -- one
+// barrier pair per column, dot products read from global memory inside the dependent loop -- took 245 us per launch,
+// 18 % of an energy + gradient call at n = 80).  All threads of a warp read the same G entry in the same iteration.
 __global__ void k_larft(const double* __restrict__ G, int ldg, const double* __restrict__ tau, int k, double* T, int ldt) {
   extern __shared__ double sh[];
-  G += (long long)blockIdx.x * ldg * k;   // one CTA per panel: G, T are (k, k, panel), tau is (k, panel)
+  G += (long long)blockIdx.x * ldg * k;   // G, T are (k, k, panel), tau is (k, panel)
   T += (long long)blockIdx.x * ldt * k;
   tau += (long long)blockIdx.x * k;
-  double* Ts = sh;            // k x k
-  double* col = sh + k * k;   // k
+  const int ldr = k + 1;
   const int t = threadIdx.x;
-  for (int idx = t; idx < k * k; idx += blockDim.x) Ts[idx] = 0.0;
-  __syncthreads();
-  for (int i = 0; i < k; ++i) {
-    const double ti = tau[i];
-    // col[0:i] = -ti * Ts[0:i, 0:i] * G[0:i, i]
-    if (t < i) {
-      double s = 0.0;
-      for (int q = t; q < i; ++q) s += Ts[t + q * k] * G[q + i * ldg];   // Ts upper triangular: q >= t
-      col[t] = -ti * s;
+  if (t < k) {
+    double* row = sh + (size_t)t * ldr;
+    for (int q = 0; q < t; ++q) row[q] = 0.0;
+    row[t] = tau[t];
+    for (int c = t + 1; c < k; ++c) {
+      const double* gc = G + (long long)c * ldg;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int q = c - 1;
+      for (; q >= t + 3; q -= 4) {
+        s0 = fma(row[q], __ldg(gc + q), s0);
+        s1 = fma(row[q - 1], __ldg(gc + q - 1), s1);
+        s2 = fma(row[q - 2], __ldg(gc + q - 2), s2);
+        s3 = fma(row[q - 3], __ldg(gc + q - 3), s3);
+      }
+      for (; q >= t; --q) s0 = fma(row[q], __ldg(gc + q), s0);
+      row[c] = -__ldg(tau + c) * ((s0 + s1) + (s2 + s3));
     }
-    __syncthreads();
-    if (t < i) Ts[t + i * k] = col[t];
-    if (t == 0) Ts[i + i * k] = ti;
-    __syncthreads();
   }
-  for (int idx = t; idx < k * k; idx += blockDim.x) T[(idx % k) + (long long)(idx / k) * ldt] = Ts[idx];
+  __syncthreads();
+  for (int idx = t; idx < k * k; idx += blockDim.x) {
+    const int i = idx % k, j = idx / k;
+    T[i + (long long)j * ldt] = sh[(size_t)i * ldr + j];
+  }
 }
 
 __global__ void k_gather_cols(const double* __restrict__ Q, long long ldq, const int* __restrict__ perm,
@@ -1265,7 +1274,7 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
   const int kb = opt_i(c, "TNAD_APPLYQ_NB", 128) >= 128 ? 128 : 64;   // measured: 128 wins at n = 2048 (2.5 vs 3.4 ms) and 6400 (46 vs 66 ms)
   const int64_t npan = (nref + kb - 1) / kb;
   TNAD_REQUIRE(npan * kb <= sytrd_vcols(n), "apply_q: reflector store too narrow");
-  TNAD_CUDA(cudaFuncSetAttribute(k_larft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kb * kb + kb) * sizeof(double))));
+  TNAD_CUDA(cudaFuncSetAttribute(k_larft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kb * kb + kb) * sizeof(double))));   // k rows of k + 1
   double* V = const_cast<double*>(Vh);
   Tens Vall;   // (row, panel, column in panel)
   Vall.p = V;
@@ -1294,7 +1303,7 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
 //   reduce          A -> tridiagonal T (one- or two-stage) and the eigen-decomposition of T by divide and conquer
 //   backtransform   columns [col0, col0 + ncols) of Z <- Q Z   (independent per column)
 //   finish          sort by |lambda|, V = U sign(lambda), canonical column signs
-void symeig_reduce(tnad_ctx* c, Tens& Aw, int64_t n, EigFactor& f) {
+void symeig_reduce(tnad_ctx* c, Tens& Aw, int64_t n, EigFactor& f, bool want_q) {
   cudaStream_t st = c->stream;
   // scale to max|a_ij| = 1 (the reflector norms are plain sums of squares; LAPACK rescales inside dlarfg instead)
   double amax = 0.0;
@@ -1327,7 +1336,58 @@ void symeig_reduce(tnad_ctx* c, Tens& Aw, int64_t n, EigFactor& f) {
     if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
     f.V2 = t_alloc(c, {f.ldv2, n - 2}, true);
     f.tau2 = t_alloc(c, {NP, n - 2}, true);
-    sb2st(c, AB.p, 33, n, dd.p, ee.p, f.V2.p, f.ldv2, f.tau2.p);   // B = Q2 T Q2'
+    // Explicit-Q mode: the chase (one cluster, latency bound) and most of the divide and conquer leave the device idle.
+    // Q1 = (stage-1 reflectors) I is formed on stream2 while the chase runs, Q2 = (chase reflectors) I and Qfull = Q1 Q2
+    // while the divide and conquer runs; the back-transformation is then a single product Qfull Z instead of the
+    // reflector passes (n = 2048: 4.8 ms of back-transformation after the divide and conquer become about 2 ms).
+    const int xq = opt_i(c, "TNAD_EXPLICIT_Q", 2);
+    const bool explicit_q = want_q && xq > 0 && c->stream2 && n <= opt_i(c, "TNAD_EXPLICITQ_MAX", 4096);
+    cudaStream_t side = c->stream2;
+    cudaEvent_t e_band = nullptr, e_chase = nullptr;
+    if (explicit_q) {
+      f.Q1x = t_alloc(c, {n, n});
+      f.Q2x = t_alloc(c, {n, n});
+      f.Qfull = t_alloc(c, {n, n});
+      e_band = get_event(c);
+      e_chase = get_event(c);
+      f.q_ready = get_event(c);
+      TNAD_CUDA(cudaEventRecord(e_band, st));      // stage-1 reflectors and the three buffers exist
+    }
+    auto on_side = [&](auto&& body) {              // enqueue `body` on stream2 (allocations inside follow that stream)
+      c->stream = side;
+      try {
+        body();
+      } catch (...) {
+        c->stream = st;
+        c->gemm_grid_cap = 0;
+        throw;
+      }
+      c->stream = st;
+      c->gemm_grid_cap = 0;
+    };
+    std::function<void(int)> overlap;
+    if (explicit_q)
+      overlap = [&](int chase_ctas) {
+        on_side([&] {
+          TNAD_CUDA(cudaStreamWaitEvent(side, e_band, 0));
+          c->gemm_grid_cap = std::max(8, c->num_sms - chase_ctas);   // the chase keeps its SMs: persistent grids stay off them
+          set_identity(c, f.Q1x.p, n, n);
+          apply_q(c, f.Vh.p, n, f.tau.p, n, f.Q1x.p, n, n, 32);
+        });
+      };
+    sb2st(c, AB.p, 33, n, dd.p, ee.p, f.V2.p, f.ldv2, f.tau2.p, overlap);   // B = Q2 T Q2'
+    if (explicit_q) {
+      TNAD_CUDA(cudaEventRecord(e_chase, st));
+      on_side([&] {
+        TNAD_CUDA(cudaStreamWaitEvent(side, e_chase, 0));
+        set_identity(c, f.Q2x.p, n, n);
+        apply_q2(c, f.V2.p, f.ldv2, f.tau2.p, n, f.Q2x.p, n, n);
+        contract(c, "ik,kj->ij", f.Q1x, f.Q2x, f.Qfull);
+        TNAD_CUDA(cudaEventRecord(f.q_ready, side));
+      });
+      c->event_pool.push_back(e_band);
+      c->event_pool.push_back(e_chase);
+    }
   } else {
     sytrd(c, Aw.p, n, n, f.Vh.p, n, f.tau.p, dd.p, ee.p);
     if (debug) TNAD_CUDA(cudaEventRecord(ev[1], st));
@@ -1358,7 +1418,14 @@ void symeig_backtransform(tnad_ctx* c, const EigFactor& f, double* Zc, int64_t l
     for (auto& e : ev) e = get_event(c);
     TNAD_CUDA(cudaEventRecord(ev[0], c->stream));
   }
-  if (f.two_stage) {
+  if (f.Qfull.p) {
+    // explicit-Q mode: one product, through a temporary (the reflector passes work in place)
+    TNAD_CUDA(cudaStreamWaitEvent(c->stream, f.q_ready, 0));
+    if (debug) TNAD_CUDA(cudaEventRecord(ev[1], c->stream));
+    Tens X = view2(Zc, f.n, ncols, ldz);
+    Tens Y = contract_new(c, "ik,kj->ij", f.Qfull, X);
+    tcopy(c, Y, X);
+  } else if (f.two_stage) {
     apply_q2(c, f.V2.p, f.ldv2, f.tau2.p, f.n, Zc, ldz, ncols);
     if (debug) TNAD_CUDA(cudaEventRecord(ev[1], c->stream));
     apply_q(c, f.Vh.p, f.n, f.tau.p, f.n, Zc, ldz, ncols, 32);
@@ -1378,8 +1445,9 @@ void symeig_backtransform(tnad_ctx* c, const EigFactor& f, double* Zc, int64_t l
 }
 
 // Zfull: the back-transformed N x N eigenvector matrix (ld N).  U, S, V as LinearAlgebra.svd returns them for a symmetric matrix.
-SvdResult symeig_finish(tnad_ctx* c, const EigFactor& f, const double* Zfull) {
+SvdResult symeig_finish(tnad_ctx* c, const EigFactor& f, const double* Zfull, int64_t ldz) {
   const int64_t n = f.n, N = f.N;
+  if (ldz <= 0) ldz = N;
   cudaStream_t st = c->stream;
   const std::vector<double>& lh = f.lam;
   // the N - n pad eigenvalues are the largest ones (stedc puts them above 3 |T|)
@@ -1406,7 +1474,7 @@ SvdResult symeig_finish(tnad_ctx* c, const EigFactor& f, const double* Zfull) {
   res.U = t_alloc(c, {n, n});
   res.V = t_alloc(c, {n, n});
   res.S = t_alloc(c, {n});
-  k_gather_cols<<<(int)n, 128, 0, st>>>(Zfull, N, dperm, dsgn, n, res.U.p, res.V.p);
+  k_gather_cols<<<(int)n, 128, 0, st>>>(Zfull, ldz, dperm, dsgn, n, res.U.p, res.V.p);
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
   TNAD_CUDA(cudaMemcpyAsync(res.S.p, dsval, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1432,7 +1500,30 @@ SvdResult svd_symmetric_dc(tnad_ctx* c, const Tens& A, bool sym_add_transpose) {
   Tens Aw;
   load_symmetric(c, A, sym_add_transpose, Aw);
   EigFactor f;
-  symeig_reduce(c, Aw, A.dim[0], f);
+  symeig_reduce(c, Aw, A.dim[0], f, true);
+  if (f.Qfull.p) {
+    // U0 = Qfull Z[0:n, :] straight into a fresh buffer (leading dimension n); the pad rows of Z are not needed
+    const bool debug = opt_i(c, "TNAD_DC_DEBUG", 0) != 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (debug) {
+      for (auto& e : ev) e = get_event(c);
+      TNAD_CUDA(cudaEventRecord(ev[0], c->stream));
+    }
+    TNAD_CUDA(cudaStreamWaitEvent(c->stream, f.q_ready, 0));
+    Tens X = view2(f.Z.p, f.n, f.N, f.N);
+    Tens U0 = contract_new(c, "ik,kj->ij", f.Qfull, X);
+    if (debug) {
+      TNAD_CUDA(cudaEventRecord(ev[1], c->stream));
+      TNAD_CUDA(cudaEventSynchronize(ev[1]));
+      float a = 0;
+      cudaEventElapsedTime(&a, ev[0], ev[1]);
+      fprintf(stderr, "  wait for Qfull + Qfull * Z %.2f ms\n", a);
+      for (auto& e : ev) c->event_pool.push_back(e);
+    }
+    SvdResult r = symeig_finish(c, f, U0.p, f.n);
+    c->event_pool.push_back(f.q_ready);
+    return r;
+  }
   symeig_backtransform(c, f, f.Z.p, f.N, f.N);
   return symeig_finish(c, f, f.Z.p);
 }
