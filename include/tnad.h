@@ -227,11 +227,13 @@ TNAD_API int tnad_host_free(tnad_ctx* ctx, double* hptr);
 TNAD_API int tnad_timer_start(tnad_ctx* ctx);
 TNAD_API int tnad_timer_stop(tnad_ctx* ctx, double* ms);
 /* per-kernel-family device time: enable, run, then read (16 slots).  families: 0 jacobi_gram, 1 one-stage
- * tridiagonalisation panel / Jacobi pivot kernels, 2 jacobi_update, 3 gemm_dmma (every einsum contraction and the GEMMs
+ * tridiagonalisation panel / Jacobi pivot kernels, 2 jacobi_update, 3 gemm_tma / gemm_dmma (every einsum contraction and the GEMMs
  * of the back-transformation and of the divide and conquer), 4 other, 5/6 work counters of the Jacobi kernels,
  * 7 k_chase (band -> tridiagonal), 8 k_q2_stage (back-transformation with Q2), 9 k_panel_gram / k_panel_qr (panel QR of the
  * band reduction), 10 k_symm_y (+ k_reduce_g), 11 k_rank64_update, 12 divide-and-conquer kernels other than its GEMMs.
- * ms[i] = summed duration, count[i] = launches. */
+ * ms[i] = summed duration, count[i] = launches.  Slots 13 / 14 describe family 3: ms[13] = sum of 2 M N K batch over its
+ * launches, ms[14] = the part of it on the TMA kernel, count[13] / count[14] = products on the TMA kernel / on the cp.async
+ * kernel. */
 TNAD_API int tnad_set_kernel_timing(tnad_ctx* ctx, int enable);
 TNAD_API int tnad_kernel_timing(tnad_ctx* ctx, double* ms /* [16] */, int64_t* count /* [16] */);
 /* FP64 tensor-core (DMMA m8n8k4) issue-rate microbenchmark: register-resident operands, no memory

@@ -217,6 +217,7 @@ class Context:
         out = {n: dict(ms=ms[i], launches=int(cnt[i])) for i, n in names.items()}
         out["m_update"]["blocks"] = int(cnt[5])     # executed 64x64 two-sided block updates (2 x 2*64^3 flop each)
         out["q_update"]["slabs"] = int(cnt[6])      # executed 128x64 panel rotations (2*128*64*64 flop each)
+        out["gemm"].update(flops=ms[13], flops_tma=ms[14], launches_tma=int(cnt[13]), launches_cp_async=int(cnt[14]))
         return out
 
     def dmma_peak(self) -> float:

@@ -90,6 +90,7 @@ struct tnad_ctx {
   int* gemm_cnt[2] = {nullptr, nullptr};   // split-K tile counters of the TMA GEMM kernel (zero between launches); [1]: products enqueued on stream2
   int gemm_grid_cap = 0;       // > 0: persistent GEMM grids use at most this many CTAs (side-stream work next to a kernel that owns SMs)
   int64_t gemm_tma_n = 0, gemm_fallback_n = 0;   // products on the TMA kernel / on the cp.async kernel
+  double gemm_flops = 0.0, gemm_tma_flops = 0.0; // 2 M N K batch of the products launched while kernel timing is on
   // A/B switches: every TNAD_* environment variable is read ONCE at tnad_create into this table; tnad_set_option
   // changes an entry afterwards.  Nothing on the hot path calls getenv.
   std::map<std::string, std::string> opts;

@@ -360,8 +360,11 @@ void launch_layout(tnad_ctx* c, const GemmDesc& d) {
 
 void gemm_run(tnad_ctx* c, const GemmDesc& d0) {
   if (d0.M <= 0 || d0.N <= 0 || d0.batch <= 0) return;
+  const double flops = 2.0 * d0.M * (double)d0.N * d0.K * d0.batch;
+  if (c->ktiming) c->gemm_flops += flops;
   if (gemm_tma_try(c, d0)) {
     c->gemm_tma_n++;
+    if (c->ktiming) c->gemm_tma_flops += flops;
     return;
   }
   c->gemm_fallback_n++;

@@ -92,6 +92,8 @@ int tnad_set_kernel_timing(tnad_ctx* c, int enable) {
   }
   c->kspans.clear();
   c->ktiming = enable != 0;
+  c->gemm_flops = c->gemm_tma_flops = 0.0;
+  c->gemm_tma_n = c->gemm_fallback_n = 0;
   TNAD_CUDA(cudaMemsetAsync(c->scal + 20, 0, 2 * sizeof(double), c->stream));
   sync(c);
   API_END(c)
@@ -118,6 +120,11 @@ int tnad_kernel_timing(tnad_ctx* c, double* ms, int64_t* count) {
   sync(c);
   count[5] = (int64_t)wc[0];
   count[6] = (int64_t)wc[1];
+  // GEMM family: algorithmic flops and the split between the TMA kernel and the cp.async kernel (unused family slots)
+  ms[13] = c->gemm_flops;
+  ms[14] = c->gemm_tma_flops;
+  count[13] = c->gemm_tma_n;
+  count[14] = c->gemm_fallback_n;
   API_END(c)
 }
 
