@@ -38,7 +38,19 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile what is stale and link; serialised across processes by a file lock (N ranks of one node importing the
+    package at the same time must not compile into the same object files)."""
+    import fcntl
     os.makedirs(OBJDIR, exist_ok=True)
+    with open(os.path.join(OBJDIR, ".lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
