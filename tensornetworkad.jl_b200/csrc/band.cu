@@ -503,6 +503,7 @@ struct Q2Args {
   double* sout;                 // stream to the next stage, null for the last stage
   long long lds;
   int s_top;                    // first (largest) sweep index processed; s_top + 1 is a multiple of 32
+  int ident;                    // X is the identity on entry: a column block is untouched by the sweeps below its last unit row
 };
 
 // Thread = (slot, half, column pair): 16 rows of 2 columns in registers, its half of the reflector cached in registers for
@@ -578,10 +579,14 @@ __global__ void __launch_bounds__(Q2_NT, 1) k_q2_stage(const Q2Args a) {
   for (int i = tid; i < NB * QC; i += Q2_NT) (&topbuf[0][0])[i] = 0.0;     // columns beyond ncols stay 0
   __syncthreads();
 
+  // X = I: columns c0 .. c0 + 15 are zero below row c0 + 15 and sweep s only touches rows >= s + 1, so this column block
+  // starts at sweep c0 + 14 (rounded up to the register-shift period); every later stage starts one period earlier than
+  // the stage above it, so that the stream rows it consumes have been written (half of the work of the pass is skipped)
+  const int s_first = a.ident ? min(a.s_top, (blockIdx.x * QC + QC + 2) / UNR * UNR - 1 + UNR - UNR * (a.q0 / QS + 1)) : a.s_top;
 #pragma unroll
-  for (int i = 0; i < NB - 1; ++i) stage_v(a.s_top - i, i);
+  for (int i = 0; i < NB - 1; ++i) stage_v(s_first - i, i);
   int par = 0;
-  for (int sb = a.s_top; sb >= 0; sb -= UNR) {
+  for (int sb = s_first; sb >= 0; sb -= UNR) {
 #pragma unroll
     for (int r = 0; r < UNR; ++r) {
       const int s = sb - r;
@@ -1557,7 +1562,8 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
 }
 
 // X[0:n, 0:ncols] <- Q2 X (reflectors of sb2st)
-void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, int64_t n, double* X, int64_t ldx, int64_t ncols) {
+void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, int64_t n, double* X, int64_t ldx, int64_t ncols,
+              bool x_is_identity) {
   if (n < 3 || ncols <= 0) return;
   const int NP = (int)chase_positions(n);
   const int nst = (NP + QS - 1) / QS;
@@ -1576,6 +1582,7 @@ void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, in
     a.sin = k == 0 ? nullptr : ((k & 1) ? sa.p : sb.p);
     a.sout = k == nst - 1 ? nullptr : ((k & 1) ? sb.p : sa.p);
     a.lds = lds;
+    a.ident = x_is_identity ? 1 : 0;
     // the first slot of the stage is active for sweeps s <= n - 2 - 32 q0 only: later (= earlier in time) sweeps are skipped
     a.s_top = (int)std::min<int64_t>(s_top, ((n - 1 - (int64_t)CB * a.q0) + 31) / 32 * 32 - 1);
     KTimer kt(c, KF_Q2);

@@ -23,7 +23,9 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
 // overlap(ctas): called right after the chase kernel is launched (it occupies `ctas` SMs) and before the host waits for it
 void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, double* ee, double* V2, int64_t ldv, double* tau2,
            const std::function<void(int)>& overlap = {});
-void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, int64_t n, double* X, int64_t ldx, int64_t ncols);
+// x_is_identity: X = I (n x n) on entry -- the pass skips the sweeps that only see zeros
+void apply_q2(tnad_ctx* c, const double* V2, int64_t ldv, const double* tau2, int64_t n, double* X, int64_t ldx, int64_t ncols,
+              bool x_is_identity = false);
 // three-phase form of the direct symmetric eigensolver (reduce / back-transform a column block / finish)
 struct EigFactor {
   int64_t n = 0, N = 0, ldv2 = 0;

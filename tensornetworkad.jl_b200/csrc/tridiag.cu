@@ -1381,7 +1381,7 @@ void symeig_reduce(tnad_ctx* c, Tens& Aw, int64_t n, EigFactor& f, bool want_q) 
       on_side([&] {
         TNAD_CUDA(cudaStreamWaitEvent(side, e_chase, 0));
         set_identity(c, f.Q2x.p, n, n);
-        apply_q2(c, f.V2.p, f.ldv2, f.tau2.p, n, f.Q2x.p, n, n);
+        apply_q2(c, f.V2.p, f.ldv2, f.tau2.p, n, f.Q2x.p, n, n, opt_i(c, "TNAD_Q2_IDENT", 1) != 0);
         contract(c, "ik,kj->ij", f.Q1x, f.Q2x, f.Qfull);
         TNAD_CUDA(cudaEventRecord(f.q_ready, side));
       });

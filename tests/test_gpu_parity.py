@@ -54,6 +54,71 @@ def test_contract_linearity_at_full_size(ctx):
     assert rel(lhs[:3], np.einsum(spec, (X2a + 2.0 * X2b)[:3], bulk, optimize=True)) < 1e-13
 
 
+# Shapes the tensor-map kernel (gemm_tma.cu) accepts: k-fast / row-fast operands, two-level rows and K, batch, ragged
+# edges (zero-filled boxes), split-K with the last-arriver reduction.  Each one must agree with numpy AND with the
+# cp.async kernel (TNAD_GEMM_TMA=0) on the same operands.
+TMA_CASES = [
+    ("ab,bc->ac", (256, 128), (128, 192)), ("ab,cb->ac", (200, 96), (150, 96)), ("ba,bc->ac", (96, 200), (96, 150)),
+    ("ba,cb->ac", (96, 200), (150, 96)), ("ab,bc->ac", (130, 2048), (2048, 70)), ("ab,bc->ac", (64, 4096), (4096, 64)),
+    ("ibd,dcl->ibcl", (32, 16, 32), (32, 16, 32)), ("ibcl,jkcb->ijlk", (32, 16, 16, 32), (16, 16, 16, 16)),
+    ("abi,aed->ibed", (32, 16, 32), (32, 16, 32)), ("ibed,bjce->ijcd", (32, 16, 16, 32), (16, 16, 16, 16)),
+    ("ijcd,dck->ijk", (32, 16, 16, 32), (32, 16, 32)), ("pi,pj->ij", (2048, 48), (2048, 48)),
+    ("rpi,rpj->ijp", (300, 3, 64), (300, 3, 64)), ("ab,bc->ac", (77, 33), (33, 18)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,sa,sb", TMA_CASES)
+def test_contract_tma_kernel_vs_cp_async_kernel(ctx, opt, spec, sa, sb):
+    rng = np.random.default_rng(abs(hash((spec, sa, sb))) % 2 ** 32)
+    A, B = rng.standard_normal(sa), rng.standard_normal(sb)
+    ref = np.einsum(spec, A, B, optimize=True)
+    c_tma = ctx.contract(spec, A, B)
+    C0 = rng.standard_normal(ref.shape)
+    c_tma_ab = ctx.contract(spec, A, B, alpha=-0.5, beta=2.0, Cin=C0)
+    c_tma_again = ctx.contract(spec, A, B)
+    opt("TNAD_GEMM_TMA", "0")
+    c_old = ctx.contract(spec, A, B)
+    assert rel(c_tma, ref) < 1e-13 and rel(c_old, ref) < 1e-13
+    assert rel(c_tma_ab, -0.5 * ref + 2.0 * C0) < 1e-13
+    assert np.array_equal(c_tma, c_tma_again)           # split-K sums in a fixed order: bit-for-bit repeatable
+
+
+@pytest.mark.gpu
+def test_contract_tma_forced_split_k(ctx, opt):
+    rng = np.random.default_rng(3)
+    A, B = rng.standard_normal((128, 1024)), rng.standard_normal((1024, 192))
+    ref = A @ B
+    for s in ("1", "2", "5", "16"):
+        opt("TNAD_GEMM_SPLITK", s)
+        assert rel(ctx.contract("ab,bc->ac", A, B), ref) < 1e-13, s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [520, 1000, 1536])
+def test_svd_sym_explicit_q_same_as_reflector_passes(ctx, opt, n):
+    """Explicit-Q mode (Q1, Q2, Q1 Q2 on the side stream, one product at the end) against the reflector passes."""
+    opt("TNAD_SYMEIG", "2")
+    opt("TNAD_EIG_2STAGE", "1")
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n)); a = a + a.T
+    res = {}
+    for mode, ident in (("0", "1"), ("2", "0"), ("2", "1")):
+        opt("TNAD_EXPLICIT_Q", mode)
+        opt("TNAD_Q2_IDENT", ident)
+        res[(mode, ident)] = ctx.svd_sym(a)
+    u0, s0, v0 = res[("0", "1")]
+    for key in (("2", "0"), ("2", "1")):
+        u, s, v = res[key]
+        assert np.abs(s - s0).max() <= 1e-13 * s0[0]
+        assert np.abs((u * s) @ v.T - a).max() <= 1e-12 * s0[0], key
+        assert np.abs(u.T @ u - np.eye(n)).max() <= 1e-12, key
+        # canonical gauge: well separated vectors agree entry by entry
+        gap_ok = np.abs(np.diff(s0)) > 1e-6 * s0[0]
+        ok = np.concatenate([[True], gap_ok]) & np.concatenate([gap_ok, [True]])
+        assert np.abs(u[:, ok] - u0[:, ok]).max() <= 1e-8, key
+
+
 # ---- SVD (LinearAlgebra.svd call sites) -----------------------------------------------------------------------
 def _check_svd(ctx, A, tol_rec=5e-14):
     U, S, V = ctx.svd(A)
