@@ -1018,39 +1018,49 @@ __global__ void k_load_symm(double* dst, long long ldd, const double* __restrict
 }
 
 // Compact WY factor of one panel (dlarft, forward / columnwise): T upper triangular, H_0..H_{k-1} = I - V T V'.
-// G = V'V (k x k, ldg), one CTA per panel, thread t owns ROW t of T: T[t][c] = -tau_c sum_{t <= q < c} T[t][q] G[q][c] only
-// involves the thread's own row, so the recurrence needs no barrier and no exchange (the column-oriented form -- one
-// barrier pair per column, dot products read from global memory inside the dependent loop -- took 245 us per launch,
-// 18 % of an energy + gradient call at n = 80).  All threads of a warp read the same G entry in the same iteration.
-__global__ void k_larft(const double* __restrict__ G, int ldg, const double* __restrict__ tau, int k, double* T, int ldt) {
-  extern __shared__ double sh[];
-  G += (long long)blockIdx.x * ldg * k;   // G, T are (k, k, panel), tau is (k, panel)
+// G = V'V (k x k, ldg).  T[t][c] = -tau_c sum_{t <= q < c} T[t][q] G[q][c] only involves ROW t of T, so the rows are
+// independent: one WARP per row (grid: panels x k/16, 16 warps per CTA), lane l keeps T[t][l + 32 j] in registers, the dot
+// product of a column is a 4-term partial sum per lane + one shuffle reduction, and the G column of the next step is
+// loaded before the reduction of the current one.  (The column-oriented form -- one barrier pair per column, dot products
+// read from global memory inside the dependent loop -- took 245 us per launch, 18 % of an energy + gradient call at n = 80.)
+__global__ void __launch_bounds__(512) k_larft(const double* __restrict__ G, int ldg, const double* __restrict__ tau, int k, double* T, int ldt) {
+  G += (long long)blockIdx.x * ldg * k;   // G, T are (k, k, panel), tau is (k, panel); k <= 128
   T += (long long)blockIdx.x * ldt * k;
   tau += (long long)blockIdx.x * k;
-  const int ldr = k + 1;
-  const int t = threadIdx.x;
-  if (t < k) {
-    double* row = sh + (size_t)t * ldr;
-    for (int q = 0; q < t; ++q) row[q] = 0.0;
-    row[t] = tau[t];
-    for (int c = t + 1; c < k; ++c) {
-      const double* gc = G + (long long)c * ldg;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int q = c - 1;
-      for (; q >= t + 3; q -= 4) {
-        s0 = fma(row[q], __ldg(gc + q), s0);
-        s1 = fma(row[q - 1], __ldg(gc + q - 1), s1);
-        s2 = fma(row[q - 2], __ldg(gc + q - 2), s2);
-        s3 = fma(row[q - 3], __ldg(gc + q - 3), s3);
-      }
-      for (; q >= t; --q) s0 = fma(row[q], __ldg(gc + q), s0);
-      row[c] = -__ldg(tau + c) * ((s0 + s1) + (s2 + s3));
-    }
+  const int lane = threadIdx.x & 31, t = blockIdx.y * 16 + (threadIdx.x >> 5);
+  if (t >= k) return;
+  double tr[4] = {0.0, 0.0, 0.0, 0.0};
+  {
+    const double tt = tau[t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane + 32 * j == t) tr[j] = tt;
   }
-  __syncthreads();
-  for (int idx = t; idx < k * k; idx += blockDim.x) {
-    const int i = idx % k, j = idx / k;
-    T[i + (long long)j * ldt] = sh[(size_t)i * ldr + j];
+  double gn[4];
+  auto load_col = [&](int c, double (&g)[4]) {
+    const double* gc = G + (long long)c * ldg;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = lane + 32 * j;
+      g[j] = (c < k && q >= t && q < c) ? __ldg(gc + q) : 0.0;
+    }
+  };
+  load_col(t + 1, gn);
+  for (int c = t + 1; c < k; ++c) {
+    double g[4] = {gn[0], gn[1], gn[2], gn[3]};
+    load_col(c + 1, gn);
+    double sum = fma(tr[0], g[0], tr[1] * g[1]) + fma(tr[2], g[2], tr[3] * g[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double v = -__ldg(tau + c) * sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane + 32 * j == c) tr[j] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < k) T[t + (long long)c * ldt] = tr[j];
   }
 }
 
@@ -1274,7 +1284,6 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
   const int kb = opt_i(c, "TNAD_APPLYQ_NB", 128) >= 128 ? 128 : 64;   // measured: 128 wins at n = 2048 (2.5 vs 3.4 ms) and 6400 (46 vs 66 ms)
   const int64_t npan = (nref + kb - 1) / kb;
   TNAD_REQUIRE(npan * kb <= sytrd_vcols(n), "apply_q: reflector store too narrow");
-  TNAD_CUDA(cudaFuncSetAttribute(k_larft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kb * kb + kb) * sizeof(double))));   // k rows of k + 1
   double* V = const_cast<double*>(Vh);
   Tens Vall;   // (row, panel, column in panel)
   Vall.p = V;
@@ -1283,7 +1292,7 @@ void apply_q(tnad_ctx* c, const double* Vh, int64_t ldv, const double* tau, int6
   Vall.str[0] = 1; Vall.str[1] = (int64_t)kb * ldv; Vall.str[2] = ldv;
   Tens Gall = t_alloc(c, {kb, kb, npan}), Tall = t_alloc(c, {kb, kb, npan}), VT = t_alloc(c, {n, kb, npan});
   contract(c, "rpi,rpj->ijp", Vall, Vall, Gall);
-  k_larft<<<(int)npan, 128, (kb * kb + kb) * sizeof(double), c->stream>>>(Gall.p, kb, tau, kb, Tall.p, kb);
+  k_larft<<<dim3((unsigned)npan, (unsigned)((kb + 15) / 16)), 512, 0, c->stream>>>(Gall.p, kb, tau, kb, Tall.p, kb);
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
   contract(c, "rpi,ijp->rjp", Vall, Tall, VT);

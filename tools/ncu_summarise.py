@@ -46,7 +46,8 @@ print("\n".join(out[:22]))
 # ---- full captures
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
@@ -56,7 +57,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 full = ["# ncu --set full summaries (round 2)", "",
         "Command per kernel: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 3 -c 2 python tools/c4_trace.py 4 128 1 1`",
         "(energy + gradient at d=4, chi=128, maxit=1: the kernels of the n = 2048 eigen-decomposition and the step's contractions; the third and",
-        "fourth launch of each kernel are captured).  Raw pages: gpurun_out/r2_full_<kernel>.csv (scratch).", ""]
+        "fourth launch of each kernel are captured).  Raw pages: gpurun_out/r2_full_<kernel>.csv (scratch).",
+        "`gemm_tma_kernel`: captured from `tools/contract_bench.py 128 16 2` (-s 6 -c 6: four launches of `ibd,dcl->ibcl`, 2048 x 2048 x 128, and two of",
+        "`ibcl,jkcb->ijlk`, 16384 x 256 x 256 -- the two dominant shapes of a ctmrgstep).", ""]
 traffic = {}
 for fn in sorted(os.listdir(G)):
     m = re.match(r"r2_full_(.+)\.csv$", fn)
