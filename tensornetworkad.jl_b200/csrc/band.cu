@@ -123,14 +123,14 @@ __device__ __forceinline__ double fast_rcp_pos(double x) {
   return y;
 }
 
-__device__ __forceinline__ double warp_house(double x, int lane, double& tau, double& beta) {
-  const double xn2 = wsum(lane >= 1 ? x * x : 0.0);
-  const double alpha = __shfl_sync(0xffffffffu, x, 0);
+// reflector scalars from alpha = x_0 and xn2 = sum_{r >= 1} x_r^2: v_r = x_r * scale (v_0 = 1), H = I - tau v v'
+__device__ __forceinline__ void house_scalars(double alpha, double xn2, double& tau, double& beta, double& scale) {
   const double s2 = fma(alpha, alpha, xn2);
   if (xn2 == 0.0 || !(s2 > 1e-290 && s2 < 1e290)) {          // nothing to annihilate (or a degenerate scale): H = I
     tau = 0.0;
     beta = alpha;
-    return lane == 0 ? 1.0 : 0.0;
+    scale = 0.0;
+    return;
   }
   // one reciprocal square root and one reciprocal instead of a square root and two divisions:
   // beta = -sign(alpha) |x|, tau = (beta - alpha) / beta = 1 + |alpha| / |x|, v = x / (alpha - beta) = sign(alpha) x / (|alpha| + |x|)
@@ -140,7 +140,13 @@ __device__ __forceinline__ double warp_house(double x, int lane, double& tau, do
   beta = alpha >= 0.0 ? -nrm : nrm;
   tau = fma(aa, rn, 1.0);
   const double rc = fast_rcp_pos(aa + nrm);
-  const double scale = alpha >= 0.0 ? rc : -rc;
+  scale = alpha >= 0.0 ? rc : -rc;
+}
+__device__ __forceinline__ double warp_house(double x, int lane, double& tau, double& beta) {
+  const double xn2 = wsum(lane >= 1 ? x * x : 0.0);
+  const double alpha = __shfl_sync(0xffffffffu, x, 0);
+  double scale;
+  house_scalars(alpha, xn2, tau, beta, scale);
   return lane == 0 ? 1.0 : x * scale;
 }
 
@@ -164,7 +170,7 @@ struct ChaseArgs {
 // per-position shared memory (doubles): Ew (1 + 32*33 + 1), Dw (32*33), 7 scratch vectors of 34, mailboxes:
 //   vbox (reflector from position t-1), rbox[2] (row from position t+1, double buffered by sweep parity: the D warp may
 //   lag the E warp by one hop), dbox (reflector E warp -> D warp), and a word the D warp uses to publish its progress
-constexpr int POS_BOXES = 4 * MB_WORDS + 2;
+constexpr int POS_BOXES = 4 * MB_WORDS + 4;   // 4 mailboxes + the progress words of the D warp, of E1 and of E2 (two)
 constexpr int POS_DOUBLES = (2 + CB * WLD) + CB * WLD + CB * WLD + 7 * 34 + POS_BOXES;   // Ew, Dw, transpose scratch, vectors, boxes
 constexpr int BOXOFF = POS_DOUBLES - POS_BOXES;      // offset of a position's boxes inside its shared-memory slice
 
@@ -209,13 +215,14 @@ __device__ __forceinline__ bool flag_wait(unsigned long long* word, unsigned lon
   return true;
 }
 
-__global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
+__global__ void __launch_bounds__(384, 1) k_chase(const ChaseArgs a) {
   extern __shared__ double sm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int pw = wid >> 1;                        // position within the CTA
-  const bool is_d = (wid & 1) != 0;               // role: E warp / D warp
+  const int pw = wid / 3;                         // position within the CTA
+  const int role = wid - 3 * pw;                  // 0: E1 (reflector: the critical path), 1: D (diagonal block), 2: E2 (column sums, left-apply)
+  const bool is_d = role == 1;
   // zero the local mailboxes of every position of this CTA before any neighbour may write into them
   for (int i = threadIdx.x; i < a.W * POS_DOUBLES; i += blockDim.x) sm[i] = 0.0;
   __syncthreads();
@@ -239,6 +246,9 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
   unsigned long long* my_rbox_l = lbox + MB_WORDS;              // [2] row from t+1
   unsigned long long* dbox = lbox + 3 * MB_WORDS;               // reflector E -> D
   unsigned long long* dflag = lbox + 4 * MB_WORDS;              // D warp: number of hops whose E column is handed back
+  unsigned long long* e1flag = dflag + 1;                       // E1: number of hops whose right-applied block sits in Tw
+  unsigned long long* wflag = dflag + 2;                        // E2: number of hops whose left-apply coefficients w sit in sw
+  unsigned long long* e2flag = dflag + 3;                       // E2: number of hops it has finished with Tw
   // A mailbox lives with its READER: in the reader's shared memory when the writer sits in the same CTA or in the same
   // cluster (then the writer pushes through distributed shared memory), in global memory (L2) between clusters.
   const bool prev_cta = t > 0 && pw == 0, next_cta = t + 1 < a.NP && pw + 1 == a.W;
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
     const int p = 1 + CB * t;
     const int i = p + lane;   // my row
 #pragma unroll 4
-    for (int k = 0; k < CB; ++k) {
+    for (int k = 0; k < CB && role != 2; ++k) {
       double val = 0.0;
       if (i < n) {
         if (!is_d) {
@@ -278,12 +288,12 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
       }
       (is_d ? Dw : Ew)[lane * WLD + k] = val;
     }
-    if (t == 0 && lane == 0 && !is_d) a.d[0] = a.AB[0];
+    if (t == 0 && lane == 0 && role == 0) a.d[0] = a.AB[0];
   }
-  // both warps of the position have written their block (named barrier: 64 threads)
-  asm volatile("bar.sync %0, 64;" ::"r"(1 + pw) : "memory");
+  // the warps of the position have written their blocks (named barrier: 96 threads)
+  asm volatile("bar.sync %0, 96;" ::"r"(1 + pw) : "memory");
 
-  long long pc[6] = {0, 0, 0, 0, 0, 0};
+  long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const bool prof = a.prof != nullptr;
   const long long tstart = prof ? clock64() : 0;
 #define CH_TICK(slot)                     \
@@ -292,41 +302,59 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
       pc[slot] += _n - tk;                \
       tk = _n;                            \
     }
-  if (!is_d) {
-    // =============================================== E warp ===============================================
+  if (role == 0) {
+    // =============================================== E1 warp ==============================================
+    // right-apply of the previous reflector, the new reflector, its sends: everything position t+1 and t-1 wait for.
+    // The right-applied block goes to Tw for the E2 warp, which owns the rest of the hop.
     for (int s = 0; s < my_sweeps; ++s) {
       const unsigned seq = (unsigned)s + 1u;
       long long tk = prof ? clock64() : 0;
-      // the D warp has handed back column 31 of my block for this sweep (its hop s-1)
+      // the D warp has handed back column 31 of my block for this sweep (its hop s-1), E2 the left-apply coefficients
       if (s > 0 && !flag_wait(dflag, (unsigned long long)s, a.err)) break;
-      __threadfence_block();                     // acquire: the column the D warp stored before raising the flag
-      double ent = 0.0;                          // E'[31][31]: double 0 of the row that enters from position t+1
-      if (s > 0 && s - 1 < nx_sweeps) {
-        if (!mb_recv_one(my_rbox + ((s - 1) & 1) * MB_WORDS, (unsigned)s, 0, ent, a.err)) break;
-      }
+      if (s > 0 && t > 0 && !flag_wait(wflag, (unsigned long long)s, a.err)) break;
+      __threadfence_block();                     // acquire: what the two warps stored before raising their flags
       CH_TICK(0)
       double v, tau, beta;
       double Er[CB];
-      double e0 = 0.0;                           // row 0 of the block after the right-apply, column `lane`
       double fr = 0.0;                           // coefficient of my row in the right-apply
+      const bool row_enters = s > 0 && s - 1 < nx_sweeps;
       if (t == 0) {
         double x = Ew[lane * WLD + (CB - 1)];
+        double ent = 0.0;
+        if (row_enters && !mb_recv_one(my_rbox + ((s - 1) & 1) * MB_WORDS, (unsigned)s, 0, ent, a.err)) break;
         if (s > 0 && lane == CB - 1) x = ent;
         v = warp_house(x, lane, tau, beta);
         if (lane == 0) a.e[s] = beta;
       } else {
+        // Everything that does not depend on beta of position t+1 (= E'[31][31], the only non-zero of the entering row 31)
+        // happens BEFORE the wait for it: the block, the previous reflector, the dot products and reflector inputs of
+        // rows 0 .. 30 and their sum of squares.  After the wait only row 31's entry and the scalars are left, so this
+        // position's share of the loop t -> t+1 -> t is a dozen dependent operations instead of a 32-term dot product
+        // and a five-level shuffle reduction.
+        // The block of this sweep, straight into registers: row r of it is row r + 1 of the previous sweep's right-applied
+        // block (Tw, written by this warp) after the left-apply with the previous reflector (sv) and the coefficients w
+        // (sw, from E2), shifted by one column; column 31 is what the D warp handed back; row 31 enters as zeros + beta.
+        if (s == 0) {
 #pragma unroll
-        for (int k = 0; k < CB; ++k) Er[k] = Ew[lane * WLD + k];
-        if (s > 0 && lane == CB - 1) {
+          for (int k = 0; k < CB; ++k) Er[k] = Ew[lane * WLD + k];
+        } else if (lane == CB - 1) {
 #pragma unroll
-          for (int k = 0; k < CB - 1; ++k) Er[k] = 0.0;
-          Er[CB - 1] = ent;
+          for (int k = 0; k < CB; ++k) Er[k] = 0.0;
+        } else {
+          const double vr = sv[lane + 1];
+          double tw[CB], wk[CB];                   // all loads first
+#pragma unroll
+          for (int k = 0; k < CB - 1; ++k) {
+            tw[k] = Tw[(lane + 1) * WLD + k + 1];
+            wk[k] = sw[k + 1];
+          }
+#pragma unroll
+          for (int k = 0; k < CB - 1; ++k) Er[k] = fma(-vr, wk[k], tw[k]);
+          Er[CB - 1] = Ew[lane * WLD + (CB - 1)];
         }
-        const double e0k = Ew[lane];               // row 0 of the block seen by columns: the row that will leave
         CH_TICK(2)
         if (!mb_recv(my_vbox, seq, svp, lane, a.err)) break;
         CH_TICK(1)
-        e0 = e0k;
         const double taup = svp[CB];
         double dot0 = 0.0, dot1 = 0.0, dot2 = 0.0, dot3 = 0.0;
 #pragma unroll
@@ -337,64 +365,96 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
           dot3 = fma(Er[k + 3], svp[k + 3], dot3);
         }
         fr = taup * ((dot0 + dot1) + (dot2 + dot3));
-        Er[0] = fma(-fr, svp[0], Er[0]);           // only column 0 of the right-apply sits in front of the reflector
-        v = warp_house(Er[0], lane, tau, beta);
-        // beta is E'[31][31] of position t-1's next sweep -- all its E warp needs of the leaving row: send it before the
-        // column sums (the loop t -> t+1 -> t closes here: dot, reflector, two links)
+        double x = fma(-fr, svp[0], Er[0]);        // column 0 after the right-apply (rows 0 .. 30; row 31 follows)
+        const double pre = wsum(lane >= 1 ? x * x : 0.0);
+        const double alpha = __shfl_sync(0xffffffffu, x, 0);
+        double xn2 = pre;
+        CH_TICK(6)
+        if (s > 0) {
+          double ent = 0.0;
+          if (row_enters && !mb_recv_one(my_rbox + ((s - 1) & 1) * MB_WORDS, (unsigned)s, 0, ent, a.err)) break;
+          CH_TICK(7)
+          const double f31 = taup * ent * svp[CB - 1], x31 = -f31 * svp[0];
+          xn2 = fma(x31, x31, pre);
+          if (lane == CB - 1) {
+            Er[CB - 1] = ent;
+            fr = f31;
+            x = x31;
+          }
+        }
+        double scale;
+        house_scalars(alpha, xn2, tau, beta, scale);
+        Er[0] = x;
+        v = lane == 0 ? 1.0 : x * scale;
+        // beta is E'[31][31] of position t-1's next sweep -- all its E1 warp needs of the leaving row (the loop
+        // t -> t+1 -> t closes here)
         if (lane == 0) mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, 0, beta);
       }
-      // reflector out at once: to my D warp and to position t+1
+      // reflector out at once: to position t+1 and to my D warp
       if (s < nx_sweeps) {
         mb_send(nx_vbox, seq, lane, v);
         if (lane == 0) mb_send(nx_vbox, seq, CB, tau);
       }
       mb_send(dbox, seq, lane, v);
       if (lane == 0) mb_send(dbox, seq, CB, tau);
-      if (t > 0) {                                 // the rest of the right-apply
+      CH_TICK(8)
+      if (t > 0) {
+        // the rest of the right-apply, then the block, the reflector and tau to the E2 warp
 #pragma unroll
         for (int k = 1; k < CB; ++k) Er[k] = fma(-fr, svp[k], Er[k]);
-        e0 = fma(-__shfl_sync(0xffffffffu, fr, 0), svp[lane], e0);     // row 0 after the right-apply, one column per lane
-      }
-      double wl = 0.0;
-      if (t > 0) {
-        // column sums c_k = sum_r v_r E[r][k]: every lane stores its weighted row, lane k adds up column k (a transposition
-        // through shared memory: 80 instructions instead of the 217 of a recursive-halving shuffle tree -- the warp is
-        // alone on its scheduler, so the instruction count is the latency)
+        if (s > 0 && !flag_wait(e2flag, (unsigned long long)s, a.err)) break;      // E2 has read row 0 of Tw (the leaving row)
 #pragma unroll
-        for (int k = 0; k < CB; ++k) Tw[lane * WLD + k] = v * Er[k];
+        for (int k = 0; k < CB; ++k) Tw[lane * WLD + k] = Er[k];
+        sv[lane] = v;
+        if (lane == 0) sv[CB] = tau;
         __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          *(volatile unsigned long long*)e1flag = (unsigned long long)(s + 1);
+        }
+      }
+      CH_TICK(4)
+      a.V2[(long long)s * a.ldv + CB * t + lane] = v;
+      if (lane == 0) a.tau2[(long long)s * a.NP + t] = tau;
+      CH_TICK(3)
+    }
+  } else if (role == 2) {
+    // =============================================== E2 warp ==============================================
+    // column sums c_k = sum_r v_r E[r][k] (lane k walks down column k of Tw) -> the left-apply coefficients w for E1, and
+    // the E part of the row that leaves to position t-1
+    if (t > 0)
+      for (int s = 0; s < my_sweeps; ++s) {
+        const unsigned seq = (unsigned)s + 1u;
+        long long tk = prof ? clock64() : 0;
+        if (!flag_wait(e1flag, (unsigned long long)(s + 1), a.err)) break;
+        __threadfence_block();
+        CH_TICK(0)
+        const double tau = sv[CB];
         double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
         for (int r = 0; r < CB; r += 4) {
-          c0 += Tw[r * WLD + lane];
-          c1 += Tw[(r + 1) * WLD + lane];
-          c2 += Tw[(r + 2) * WLD + lane];
-          c3 += Tw[(r + 3) * WLD + lane];
+          c0 = fma(sv[r], Tw[r * WLD + lane], c0);
+          c1 = fma(sv[r + 1], Tw[(r + 1) * WLD + lane], c1);
+          c2 = fma(sv[r + 2], Tw[(r + 2) * WLD + lane], c2);
+          c3 = fma(sv[r + 3], Tw[(r + 3) * WLD + lane], c3);
         }
-        wl = lane == 0 ? 0.0 : tau * ((c0 + c1) + (c2 + c3));
-        // the E part of the row that leaves to position t-1 (v_0 = 1): E[0][k] - w_k, straight from lane k
-        CH_TICK(2)
-        if (lane >= 1) mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, lane, e0 - wl);
-        CH_TICK(4)
-      }
-      // off the critical path: reflector store, left-apply, shifted block of the next sweep
-      a.V2[(long long)s * a.ldv + CB * t + lane] = v;
-      if (lane == 0) a.tau2[(long long)s * a.NP + t] = tau;
-      if (t > 0) {
+        const double wl = lane == 0 ? 0.0 : tau * ((c0 + c1) + (c2 + c3));
         sw[lane] = wl;
         __syncwarp();
-        double wk[CB];                             // all loads first: the stores below may alias sw for the compiler
-#pragma unroll
-        for (int k = 1; k < CB; ++k) wk[k] = sw[k];
-        if (lane >= 1) {
-          double* dst = Ew + (lane - 1) * WLD - 1;
-#pragma unroll
-          for (int k = 1; k < CB; ++k) dst[k] = fma(-v, wk[k], Er[k]);     // column 0 is annihilated: not stored
+        if (lane == 0) {
+          __threadfence_block();
+          *(volatile unsigned long long*)wflag = (unsigned long long)(s + 1);      // E1 may build the block of sweep s + 1
         }
+        CH_TICK(2)
+        // v_0 = 1: the leaving row is E[0][k] - w_k, straight from lane k (double 0, beta, went out from E1)
+        if (lane >= 1) mb_send(pv_rbox + (s & 1) * MB_WORDS, seq, lane, Tw[lane] - wl);
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          *(volatile unsigned long long*)e2flag = (unsigned long long)(s + 1);
+        }
+        CH_TICK(3)
       }
-      __syncwarp();
-      CH_TICK(3)
-    }
   } else {
     // =============================================== D warp ===============================================
     double Dlast0 = 0.0, Dlast1 = 0.0;   // D[1][0], D[1][1] of position 0 after its last hop
@@ -471,7 +531,7 @@ __global__ void __launch_bounds__(256, 1) k_chase(const ChaseArgs a) {
   }
   if (prof && lane == 0) {
     pc[5] = clock64() - tstart;
-    for (int i = 0; i < 6; ++i) a.prof[((long long)t * 2 + (is_d ? 1 : 0)) * 6 + i] = pc[i];
+    for (int i = 0; i < 10; ++i) a.prof[((long long)t * 3 + role) * 10 + i] = pc[i];
   }
   }   // t < NP
   cluster.sync();   // no CTA may exit while a neighbour can still push into its mailboxes
@@ -1494,7 +1554,7 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   const int NP = (int)chase_positions(n);
   int W = std::max(1, std::min(4, opt_i(c, "TNAD_CHASE_W", 4)));
   while ((NP + W - 1) / W > c->num_sms) ++W;      // all CTAs must be co-resident (one per SM)
-  TNAD_REQUIRE(W <= 4, "sb2st: matrix too large for the chase kernel (n <= 32 * 4 * #SMs)");   // 2 W warps per CTA, 256 threads
+  TNAD_REQUIRE(W <= 4, "sb2st: matrix too large for the chase kernel (n <= 32 * 4 * #SMs)");   // 3 W warps per CTA, 384 threads
   const int G = (NP + W - 1) / W;
   Tens gbox = t_alloc(c, {(int64_t)NP * 3 * MB_WORDS}, true);
   Tens err = t_alloc(c, {2}, true);
@@ -1504,7 +1564,7 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   a.gbox = reinterpret_cast<unsigned long long*>(gbox.p);
   a.err = reinterpret_cast<int*>(err.p);
   const bool prof = opt_i(c, "TNAD_DC_DEBUG", 0) >= 2;
-  Tens pbuf = t_alloc(c, {(int64_t)NP * 12 + 2}, true);
+  Tens pbuf = t_alloc(c, {(int64_t)NP * 30 + 2}, true);
   a.prof = prof ? reinterpret_cast<long long*>(pbuf.p) : nullptr;
   const size_t smem = (size_t)W * POS_DOUBLES * sizeof(double);
   TNAD_CUDA(cudaFuncSetAttribute(k_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1517,7 +1577,7 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   TNAD_REQUIRE(Gp <= c->num_sms, "sb2st: matrix too large for the chase kernel");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(Gp);
-  cfg.blockDim = dim3(64 * W);
+  cfg.blockDim = dim3(96 * W);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
   cudaLaunchAttribute at[2];
@@ -1548,15 +1608,17 @@ void sb2st(tnad_ctx* c, const double* AB, int64_t ldab, int64_t n, double* dd, d
   sync(c);
   if (herr) fail(TNAD_ERR_INTERNAL, "sb2st: the chase pipeline timed out");
   if (prof) {
-    std::vector<long long> ph((size_t)NP * 12);
+    std::vector<long long> ph((size_t)NP * 30);
     TNAD_CUDA(cudaMemcpy(ph.data(), pbuf.p, ph.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     for (int t : {0, 1, NP / 2, NP / 2 + 1}) {
       if (t >= NP) continue;
       const double ns = (double)std::max<int64_t>(1, std::min<int64_t>(n - 2, n - 1 - CB * t));
-      const long long* e = ph.data() + (size_t)t * 12;
-      const long long* d = e + 6;
-      fprintf(stderr, "[tnad dc] chase position %d (W=%d) cycles/hop  E warp: wait D+row %.0f  wait v %.0f  compute %.0f  row send %.0f  bulk %.0f | %.0f   D warp: load+row %.0f  wait v %.0f  first half %.0f  bulk %.0f | %.0f\n",
-              t, W, e[0] / ns, e[1] / ns, e[2] / ns, e[4] / ns, e[3] / ns, e[5] / ns, d[0] / ns, d[1] / ns, d[3] / ns, d[4] / ns, d[5] / ns);
+      const long long* e = ph.data() + (size_t)t * 30;
+      const long long* d = e + 10;
+      const long long* e2 = e + 20;
+      fprintf(stderr, "[tnad dc] chase position %d (W=%d) cycles/hop  E1: wait D+E2 %.0f  load %.0f  wait v %.0f  dot+sum %.0f  wait beta %.0f  scalars+sends %.0f  block to E2 %.0f  store %.0f | %.0f   D: load+row %.0f  wait v %.0f  first half %.0f  bulk %.0f | %.0f   E2: wait E1 %.0f  column sums+row %.0f  left-apply %.0f | %.0f\n",
+              t, W, e[0] / ns, e[2] / ns, e[1] / ns, e[6] / ns, e[7] / ns, e[8] / ns, e[4] / ns, e[3] / ns, e[5] / ns, d[0] / ns, d[1] / ns, d[3] / ns, d[4] / ns, d[5] / ns,
+              e2[0] / ns, e2[2] / ns, e2[3] / ns, e2[5] / ns);
     }
   }
 }
