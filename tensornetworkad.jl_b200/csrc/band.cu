@@ -31,6 +31,13 @@ namespace {
 constexpr int CB = 32;     // half bandwidth = reflector length of the chase
 constexpr int WLD = 33;    // leading dimension of the window arrays in shared memory
 
+// Programmatic dependent launch (stage 1 is a chain of six short kernels per panel: their launch latencies and set-up
+// overlap the predecessor's tail): nothing before the wait touches global memory, so the semantics are those of a plain
+// stream-ordered launch; the trigger comes first so that the successor is resident when this grid retires.
+#define PDL_ENTRY()                                              \
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  \
+  asm volatile("griddepcontrol.wait;" ::: "memory")
+
 #define LAUNCH_CHECK(c)            \
   do {                             \
     (c)->launches++;               \
@@ -786,6 +793,7 @@ constexpr double PQ_THETA = 0.0625;
 constexpr int PG_LDS = 33;
 template <int NRL>
 __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int* fb) {
+  PDL_ENTRY();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();   // CS is a power of two <= 16
   extern __shared__ double sm[];
@@ -1025,6 +1033,7 @@ __global__ void __launch_bounds__(PQ_NT, 1) k_panel_gram(const PanelArgs a, int*
 // NRL == 0: any rp (multiple of 256), the panel lives in shared memory.
 template <int NRL>
 __global__ void __launch_bounds__(PQ_NT, 1) k_panel_qr(const PanelArgs a) {
+  PDL_ENTRY();
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool prof = a.prof != nullptr;
   long long tk = prof ? clock64() : 0;
@@ -1289,6 +1298,7 @@ constexpr int SY_BM = 64, SY_BK = 64, SY_LD = SY_BK + 4;
 constexpr int SY_STAGE = SY_BK * (SY_BM + 4) + CB * SY_LD;     // doubles per stage: A tile [k][m] (ld 68) + Y tile [n][k] (ld 68)
 __global__ void __launch_bounds__(128) k_symm_y(const double* __restrict__ A, long long lda, const double* __restrict__ Y, long long ldy, int m,
                                                 int ksplit, double* __restrict__ Zpart, long long ldz, double* __restrict__ Gpart, int vec) {
+  PDL_ENTRY();
   extern __shared__ double smy[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -1400,6 +1410,7 @@ __global__ void __launch_bounds__(128) k_symm_y(const double* __restrict__ A, lo
 constexpr int RU_LD = 64 + 4;
 __global__ void __launch_bounds__(128) k_rank64_update(double* __restrict__ C, long long ldc, const double* __restrict__ L,
                                                        const double* __restrict__ R, long long ldp, int m) {
+  PDL_ENTRY();
   extern __shared__ double smu[];
   double* Ls = smu;                    // Ls[k * 68 + r]
   double* Rs = smu + 64 * RU_LD;       // Rs[k * 68 + c]
@@ -1457,6 +1468,7 @@ __global__ void __launch_bounds__(128) k_rank64_update(double* __restrict__ C, l
 
 // G0[idx] = sum over the shares (fixed order: 8 interleaved partial sums per entry, combined by a shuffle tree)
 __global__ void __launch_bounds__(256) k_reduce_g(const double* __restrict__ Gpart, int nshare, double* __restrict__ G0) {
+  PDL_ENTRY();
   const int gid = blockIdx.x * 256 + threadIdx.x;
   const int idx = gid >> 3, sub = gid & 7;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -1479,6 +1491,7 @@ __global__ void __launch_bounds__(256) k_reduce_g(const double* __restrict__ Gpa
 __global__ void __launch_bounds__(256) k_make_w(const double* __restrict__ Zpart, long long ldz, int ksplit, const double* __restrict__ Y,
                                                 long long ldy, const double* __restrict__ T, const double* __restrict__ G0, int m,
                                                 double* __restrict__ P1, double* __restrict__ P2, long long ldp) {
+  PDL_ENTRY();
   __shared__ double sT[CB][CB + 1], sM[CB][CB + 1];
   __shared__ double zr[32][CB + 1], yr[32][CB + 1];
   const int tid = threadIdx.x;
@@ -1684,6 +1697,21 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
   const size_t fixed = (size_t)(2 * PQ_MAXCS * CB + 2 * CB + 2 * PQ_NW * CB + PQ_NW * CB + 2 * CB * CB + 2 * CB) * sizeof(double);
   const bool use_regs = opt_i(c, "TNAD_PANEL_REGS", 1) != 0;
   const bool use_gram = opt_i(c, "TNAD_PANEL_GRAM", 1) != 0;
+  const bool pdl = opt_i(c, "TNAD_SY2SB_PDL", 0) != 0 && opt_i(c, "TNAD_DC_DEBUG", 0) < 2;   // measured: no gain (6.28 vs 6.20 ms at n = 2048): the kernels themselves, not the gaps between them, are the 95 us per panel
+  auto launch = [&](auto kern, dim3 grid, dim3 block, size_t smem, auto... args) {   // plain grid, optional dependent launch
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    la[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = la;
+    lc.numAttrs = pdl ? 1 : 0;
+    TNAD_CUDA(cudaLaunchKernelEx(&lc, kern, args...));
+    c->launches++;
+  };
   auto gram_smem = [](int nrl) {
     return (size_t)(CB * (PQ_NT * nrl + 4) + 4 * CB * PG_LDS + 3 * CB * CB + 3 * CB + 8) * sizeof(double);
   };
@@ -1710,10 +1738,13 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     pa.Y = Yst; pa.ldy = ldy; pa.tau = tau1; pa.T = Tb.p;
     pa.prof = prof ? reinterpret_cast<long long*>(pprof.p) : nullptr;
     pa.only_if = nullptr;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    const int nat = pdl ? 2 : 1;
     if (prof) TNAD_CUDA(cudaEventRecord(pe[0], st));
     // fast path: Gram-driven factorisation (no exchange per column); it raises fbflag[panel] when a column cancels
     int* fbp = reinterpret_cast<int*>(fbflag.p) + (j / CB);
@@ -1738,7 +1769,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
         cg_.stream = st;
         at[0].val.clusterDim.x = gcs;
         cg_.attrs = at;
-        cg_.numAttrs = 1;
+        cg_.numAttrs = nat;
         KTimer kt(c, KF_PANEL);
         if (gnrl == 1) TNAD_CUDA(cudaLaunchKernelEx(&cg_, k_panel_gram<1>, pg, fbp));
         else TNAD_CUDA(cudaLaunchKernelEx(&cg_, k_panel_gram<2>, pg, fbp));
@@ -1755,7 +1786,7 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     cfg.stream = st;
     at[0].val.clusterDim.x = CS;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = nat;
     {
       KTimer kt(c, KF_PANEL);
       if (regs && nrl == 1) TNAD_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr<1>, pa));
@@ -1772,22 +1803,20 @@ void sy2sb(tnad_ctx* c, double* A, int64_t lda, int64_t n, double* Yst, int64_t 
     ksplit = (int)std::min<int64_t>(ksplit, (m + 4 * SY_BK - 1) / (4 * SY_BK));
     {
       KTimer kt(c, KF_SYMM);
-      k_symm_y<<<dim3(nrb, ksplit), 128, 2 * SY_STAGE * sizeof(double), st>>>(A22p, lda, Yp, ldy, (int)m, ksplit, Zp.p, n, Gp.p,
-                                                                                    (n % 2 == 0 && lda % 2 == 0 && ldy % 2 == 0) ? 1 : 0);
-      LAUNCH_CHECK(c);
-      k_reduce_g<<<CB * CB * 8 / 256, 256, 0, st>>>(Gp.p, nrb * ksplit, Mb.p);
+      launch(k_symm_y, dim3(nrb, ksplit), dim3(128), 2 * SY_STAGE * sizeof(double), (const double*)A22p, (long long)lda, Yp, (long long)ldy,
+             (int)m, ksplit, Zp.p, (long long)n, Gp.p, (n % 2 == 0 && lda % 2 == 0 && ldy % 2 == 0) ? 1 : 0);
+      launch(k_reduce_g, dim3(CB * CB * 8 / 256), dim3(256), 0, (const double*)Gp.p, nrb * ksplit, Mb.p);
     }
-    LAUNCH_CHECK(c);
     if (prof) TNAD_CUDA(cudaEventRecord(pe[2], st));
-    k_make_w<<<(int)((m + 31) / 32), 256, 0, st>>>(Zp.p, n, ksplit, Yp, ldy, Tb.p, Mb.p, (int)m, P1.p, P2.p, ldpp);
-    LAUNCH_CHECK(c);
+    launch(k_make_w, dim3((unsigned)((m + 31) / 32)), dim3(256), 0, (const double*)Zp.p, (long long)n, ksplit, Yp, (long long)ldy,
+           (const double*)Tb.p, (const double*)Mb.p, (int)m, P1.p, P2.p, (long long)ldpp);
     if (prof) TNAD_CUDA(cudaEventRecord(pe[3], st));
     {
       KTimer kt(c, KF_RANK64);
       const int nt = (int)((m + 63) / 64);
-      k_rank64_update<<<dim3(nt, nt), 128, 2 * 64 * RU_LD * sizeof(double), st>>>(A22p, lda, P1.p, P2.p, ldpp, (int)m);
+      launch(k_rank64_update, dim3(nt, nt), dim3(128), 2 * 64 * RU_LD * sizeof(double), A22p, (long long)lda, (const double*)P1.p,
+             (const double*)P2.p, (long long)ldpp, (int)m);
     }
-    LAUNCH_CHECK(c);
     if (prof) {
       TNAD_CUDA(cudaEventRecord(pe[4], st));
       TNAD_CUDA(cudaEventSynchronize(pe[4]));
