@@ -219,6 +219,20 @@ TNAD_API int tnad_permute(tnad_ctx* ctx, const double* in, const int64_t* dims, 
 TNAD_API int tnad_ctmrg_finish(tnad_ctx* ctx, const double* c1, const double* e1, int D, int chi,
                                double* corner_out, double* edge_out);
 
+/* ---- chi-sharded ctmrgstep over several GPUs (one process per GPU; north_star: "at chi >= 256 the enlarged-corner GEMMs
+ * are sharded along the chi index with an NCCL all-gather over NVLink before the SVD"; replaces the OMEinsum / LAPACK calls of
+ * ctmrg.jl:126-142 on every rank).  NCCL is loaded at run time: nccl_path = path of libnccl.so.2, or NULL to use the copy the
+ * host process has already mapped.  Rank 0 obtains a 128-byte unique id, the application distributes it (MPI,
+ * torch.distributed, a file), every rank calls tnad_comm_init on its own context; tnad_comm_init(ctx, .., 0, 1) without a
+ * library makes the sharded entry point run on one GPU.  tnad_ctmrgstep_sharded: every rank passes the same bulk / corner /
+ * edge (pointer mode applies; chi divisible by the number of ranks) and receives the full corner_out / edge_out; vals (chi*D,
+ * host) and ms3 (host, optional: device ms of contractions, all-gathers, eigen-decomposition) as in tnad_ctmrgstep. */
+TNAD_API int tnad_nccl_unique_id(const char* nccl_path, unsigned char* id128);
+TNAD_API int tnad_comm_init(tnad_ctx* ctx, const char* nccl_path, const unsigned char* id128, int rank, int world);
+TNAD_API int tnad_comm_destroy(tnad_ctx* ctx);
+TNAD_API int tnad_ctmrgstep_sharded(tnad_ctx* ctx, const double* bulk, int D, const double* corner, const double* edge, int chi,
+                                    double* corner_out, double* edge_out, double* vals, double* ms3);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* pinned host memory for end-to-end runs */
 TNAD_API int tnad_host_alloc(tnad_ctx* ctx, int64_t ndoubles, double** hptr);

@@ -180,3 +180,28 @@ function trg_sweep(tensors::Vector{Array{Float64,4}}, χ::Integer, niter::Intege
     rc == 0 || error("tnad_trg_sweep: " * unsafe_string(pointer(err)))
     want_grad ? (lnZ, [reshape(grads[(i - 1) * length(tensors[1]) + 1:i * length(tensors[1])], size(tensors[1])) for i in 1:ninst]) : lnZ
 end
+
+# ---- χ-sharded ctmrgstep over the ranks of an MPI job (one process per GPU) --------------------------------------
+# rank 0 asks NCCL (dlopen'ed by the library) for a unique id, MPI carries the 128 bytes, every rank joins:
+#     id = rank == 0 ? nccl_unique_id() : zeros(UInt8, 128);  MPI.Bcast!(id, 0, comm);  comm_init(id, rank, nranks)
+function nccl_unique_id(nccl_path::Union{Nothing,String} = nothing)
+    id = zeros(UInt8, 128)
+    rc = ccall((:tnad_nccl_unique_id, libtnad), Cint, (Cstring, Ptr{UInt8}), something(nccl_path, C_NULL), id)
+    rc == 0 || error("tnad_nccl_unique_id failed ($rc)")
+    id
+end
+comm_init(id::Vector{UInt8}, rank::Integer, nranks::Integer; nccl_path::Union{Nothing,String} = nothing) =
+    check(ccall((:tnad_comm_init, libtnad), Cint, (Ptr{Cvoid}, Cstring, Ptr{UInt8}, Cint, Cint),
+                ctx(), something(nccl_path, C_NULL), id, rank, nranks))
+
+# ctmrgstep((c, t, vals), (a, χ, D)) of src/ctmrg.jl:126-153 with the contractions sliced along χ over the ranks,
+# ncclAllGather around svd(cpmat + cpmat') and a shared back-transformation; every rank passes and receives the full
+# environment (a few MB)
+function ctmrgstep_sharded(a::Array{Float64,4}, c::Matrix{Float64}, t::Array{Float64,3})
+    D, χ = size(a, 1), size(c, 1)
+    c′, t′, vals = similar(c), similar(t), Vector{Float64}(undef, χ * D)
+    GC.@preserve a c t c′ t′ vals check(ccall((:tnad_ctmrgstep_sharded, libtnad), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+        ctx(), a, D, c, t, χ, c′, t′, vals, C_NULL))
+    c′, t′, vals
+end

@@ -82,6 +82,11 @@ SIGNATURES = {
     "tnad_sytrd2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tnad_stedc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_permute": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, c_int_p, C.c_void_p]),
+    "tnad_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
+    "tnad_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "tnad_comm_destroy": (C.c_int, [C.c_void_p]),
+    "tnad_ctmrgstep_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         c_double_p, c_double_p]),
     "tnad_ctmrg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "tnad_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -494,6 +499,53 @@ class Context:
 
     def symeig_free(self, h):
         self.lib.tnad_symeig_free(h)
+
+    # ---- chi-sharded ctmrgstep inside the library (NCCL loaded at run time) ----------------------------------
+    @staticmethod
+    def nccl_library_path():
+        """libnccl.so.2 of the nvidia-nccl wheel torch uses (None: let the library find a mapped / system copy)."""
+        try:
+            import nvidia.nccl as _n
+            p = os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2")
+            return p if os.path.exists(p) else None
+        except Exception:   # noqa: BLE001
+            return None
+
+    def nccl_unique_id(self) -> bytes:
+        buf = (C.c_ubyte * 128)()
+        path = self.nccl_library_path()
+        rc = self.lib.tnad_nccl_unique_id(path.encode() if path else None, buf)
+        if rc != 0:
+            raise TnadError(rc, "tnad_nccl_unique_id failed (is NCCL loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank: int, world: int):
+        path = self.nccl_library_path()
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self.check(self.lib.tnad_comm_init(self.h, path.encode() if path else None, buf, int(rank), int(world)))
+
+    def comm_destroy(self):
+        self.lib.tnad_comm_destroy(self.h)
+
+    def ctmrgstep_sharded(self, bulk, corner, edge, timing=False):
+        """Host arrays in, host arrays out (every rank passes the same environment); returns corner, edge, vals[, ms]."""
+        D, chi = bulk.shape[0], corner.shape[0]
+        b, co, ed = farray(bulk), farray(corner), farray(edge)
+        cn, en = np.empty((chi, chi), order="F"), np.empty((chi, D, chi), order="F")
+        vals = np.empty(chi * D)
+        ms = (C.c_double * 3)()
+        self.check(self.lib.tnad_ctmrgstep_sharded(self.h, _p(b), D, _p(co), _p(ed), chi, _p(cn), _p(en),
+                                                   vals.ctypes.data_as(c_double_p), ms if timing else None))
+        return (cn, en, vals, list(ms)) if timing else (cn, en, vals)
+
+    def dev_ctmrgstep_sharded(self, pbulk, D, pcorner, pedge, chi, pcorner_out, pedge_out, timing=True):
+        """Device pointers (pointer mode DEVICE must be set by the caller); returns vals (host) and the three device times."""
+        vals = np.empty(chi * D)
+        ms = (C.c_double * 3)()
+        self.check(self.lib.tnad_ctmrgstep_sharded(self.h, C.c_void_p(pbulk), int(D), C.c_void_p(pcorner), C.c_void_p(pedge), int(chi),
+                                                   C.c_void_p(pcorner_out), C.c_void_p(pedge_out), vals.ctypes.data_as(c_double_p),
+                                                   ms if timing else None))
+        return vals, list(ms)
 
     def dev_ctmrg_finish(self, pc1, pe1, D, chi, pco, peo):
         self.check(self.lib.tnad_ctmrg_finish(self.h, C.c_void_p(pc1), C.c_void_p(pe1), int(D), int(chi),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtnad_b200.so")
-SOURCES = ["tensor.cu", "gemm.cu", "gemm_tma.cu", "contract.cu", "elementwise.cu", "jacobi.cu", "symeig.cu", "tridiag.cu", "band.cu", "stedc.cu", "drivers.cu", "capi.cu", "measure.cu"]
+SOURCES = ["tensor.cu", "gemm.cu", "gemm_tma.cu", "contract.cu", "elementwise.cu", "jacobi.cu", "symeig.cu", "tridiag.cu", "band.cu", "stedc.cu", "drivers.cu", "sharded.cu", "capi.cu", "measure.cu"]
 HEADERS = ["common.h", "drivers.h", "eigdc.h", os.path.join("..", "..", "include", "tnad.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

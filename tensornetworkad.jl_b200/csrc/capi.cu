@@ -115,6 +115,7 @@ int tnad_destroy(tnad_ctx* c) {
   }
   if (c->tstart) cudaEventDestroy(c->tstart);
   if (c->tstop) cudaEventDestroy(c->tstop);
+  tnad_comm_destroy(c);
   cudaFree(c->scal);
   for (int* p : c->gemm_cnt)
     if (p) cudaFree(p);

@@ -88,6 +88,8 @@ struct tnad_ctx {
   int num_sms = 148;
   int coop_launch = 0;         // cudaDevAttrCooperativeLaunch, queried once at tnad_create
   int* gemm_cnt[2] = {nullptr, nullptr};   // split-K tile counters of the TMA GEMM kernel (zero between launches); [1]: products enqueued on stream2
+  void* comm = nullptr;        // ncclComm_t of the chi-sharded step (tnad_comm_init; NCCL is loaded at run time)
+  int comm_rank = 0, comm_world = 0;
   int gemm_grid_cap = 0;       // > 0: persistent GEMM grids use at most this many CTAs (side-stream work next to a kernel that owns SMs)
   int64_t gemm_tma_n = 0, gemm_fallback_n = 0;   // products on the TMA kernel / on the cp.async kernel
   double gemm_flops = 0.0, gemm_tma_flops = 0.0; // 2 M N K batch of the products launched while kernel timing is on

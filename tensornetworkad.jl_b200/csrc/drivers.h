@@ -80,6 +80,10 @@ double magnetisation_readout(tnad_ctx* c, const Tens& a, const Tens& m, const Te
 void magnetisation_readout_back(tnad_ctx* c, const Tens& a, const Tens& m, const Tens& corner, const Tens& edge,
                                 const MagTape& t, double ybar, Tens& abar, Tens& mbar, Tens& cornerbar, Tens& edgebar);
 
+// chi-sharded ctmrgstep over the ranks of the context's communicator (sharded.cu)
+void ctmrg_step_sharded(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& edge, Tens& corner_out, Tens& edge_out,
+                        std::vector<double>& vals_host, double* ms);
+
 }  // namespace tnad
 
 struct tnad_tape {

@@ -649,6 +649,30 @@ def test_sharded_step_single_rank_vs_oracle(ctx, D, chi):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("D,chi", [(4, 8), (9, 12), (4, 40), (4, 160)])
+def test_ctmrgstep_sharded_library_entry_single_rank(D, chi):
+    """tnad_ctmrgstep_sharded (the chi-sharded step inside the library; NCCL only for world > 1, exercised by
+    bench_sharded.py --check on 2+ GPUs) against the oracle and the unsharded entry point."""
+    c2 = T.Context(0)
+    try:
+        c2.comm_init(None, 0, 1)
+        rng = np.random.default_rng(D * 1000 + chi)
+        bulk = rng.standard_normal((D, D, D, D))
+        bulk = bulk + np.transpose(bulk, (2, 3, 0, 1))
+        c, e = O.init_random(bulk, chi, rng)
+        cg, eg, vg, ms = c2.ctmrgstep_sharded(bulk, c, e, timing=True)
+        c1, e1, v1 = c2.ctmrgstep(bulk, c, e)
+        assert np.abs(vg - v1).max() < 1e-12 and np.abs(cg - c1).max() < 1e-11 and np.abs(eg - e1).max() < 1e-11
+        if chi * D <= 160:
+            cr, er, vr = O.ctmrgstep(bulk, c, e, signfix=True)
+            assert np.abs(vg - vr).max() < 1e-12
+            assert np.abs(cg - cr).max() < 1e-10 and np.abs(eg - er).max() < 1e-10
+        assert len(ms) == 3 and ms[2] > 0.0
+    finally:
+        c2.close()
+
+
+@pytest.mark.gpu
 def test_permute_and_svd_symmetrized_device_pointers(ctx):
     import torch
     rng = np.random.default_rng(3)
