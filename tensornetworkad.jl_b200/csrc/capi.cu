@@ -62,6 +62,7 @@ int tnad_create(int device, tnad_ctx** out) {
     for (char** e = environ; e && *e; ++e)     // A/B switches: read the environment once, here
       if (strncmp(*e, "TNAD_", 5) == 0)
         if (const char* eq = strchr(*e, '=')) c->opts[std::string(*e, eq - *e)] = std::string(eq + 1);
+    c->host_prof = opt_i(c, "TNAD_HOST_PROF", 0) != 0;
     // the main stream carries the latency-critical pivot kernels of the eigensolver: give it the highest
     // priority so its CTAs are scheduled ahead of the bulk update kernels running on streams 2 and 3
     int prio_lo = 0, prio_hi = 0;
@@ -102,6 +103,12 @@ int tnad_destroy(tnad_ctx* c) {
   }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->host_prof) {
+    static const char* nm[8] = {"contract_plan", "cudaMallocAsync", "cudaFreeAsync", "tensor-map encode (2 per product)", "TMA GEMM launch", "", "", ""};
+    for (int i = 0; i < 5; ++i)
+      fprintf(stderr, "[tnad host] %-34s %9lld calls  %8.2f ms total  %6.2f us each\n", nm[i], c->hp_n[i], c->hp_ns[i] * 1e-6,
+              c->hp_n[i] ? c->hp_ns[i] * 1e-3 / c->hp_n[i] : 0.0);
+  }
   if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->stream3) cudaStreamSynchronize(c->stream3);
   for (auto& s : c->spans) {

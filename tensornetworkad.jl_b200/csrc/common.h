@@ -90,6 +90,10 @@ struct tnad_ctx {
   int* gemm_cnt[2] = {nullptr, nullptr};   // split-K tile counters of the TMA GEMM kernel (zero between launches); [1]: products enqueued on stream2
   void* comm = nullptr;        // ncclComm_t of the chi-sharded step (tnad_comm_init; NCCL is loaded at run time)
   int comm_rank = 0, comm_world = 0;
+  // host-side time per category (TNAD_HOST_PROF=1; printed by tnad_destroy): where the enqueue time of small problems goes
+  bool host_prof = false;
+  double hp_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long hp_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int gemm_grid_cap = 0;       // > 0: persistent GEMM grids use at most this many CTAs (side-stream work next to a kernel that owns SMs)
   int64_t gemm_tma_n = 0, gemm_fallback_n = 0;   // products on the TMA kernel / on the cp.async kernel
   double gemm_flops = 0.0, gemm_tma_flops = 0.0; // 2 M N K batch of the products launched while kernel timing is on
@@ -122,14 +126,25 @@ constexpr int HPIN_SLOTS = 1 << 16;
 // --------------------------------------------------------------------------------------------
 // device buffers and tensors
 // --------------------------------------------------------------------------------------------
+// RAII host stopwatch (no-op unless tnad_ctx::host_prof): 0 plan, 1 malloc, 2 free, 3 tensor-map encode, 4 GEMM launch
+struct HostTimer {
+  tnad_ctx* c;
+  int slot;
+  long long t0;
+  HostTimer(tnad_ctx* c_, int slot_);
+  ~HostTimer();
+};
+
 struct DBuf {
   tnad_ctx* c;
   double* p;
   size_t n;
   DBuf(tnad_ctx* c_, size_t n_) : c(c_), p(nullptr), n(n_) {
+    HostTimer ht(c, 1);
     TNAD_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(double), c->stream));
   }
   ~DBuf() {
+    HostTimer ht(c, 2);
     if (p) cudaFreeAsync(p, c->stream);
   }
   DBuf(const DBuf&) = delete;

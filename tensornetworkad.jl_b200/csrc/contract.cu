@@ -179,7 +179,11 @@ GemmDesc contract_plan(const char* spec, const Tens& A, const Tens& B, const Ten
 }
 
 void contract(tnad_ctx* c, const char* spec, const Tens& A, const Tens& B, Tens& C, double alpha, double beta) {
-  GemmDesc d = contract_plan(spec, A, B, C);
+  GemmDesc d;
+  {
+    HostTimer ht(c, 0);
+    d = contract_plan(spec, A, B, C);
+  }
   d.alpha = alpha;
   d.beta = beta;
   gemm_run(c, d);

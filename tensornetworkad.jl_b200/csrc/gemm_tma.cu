@@ -564,8 +564,11 @@ bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d) {
   alignas(64) CUtensorMap mapA, mapB;
   TmaGemm g;
   memset(&g, 0, sizeof(g));
-  if (!plan_operand(d.A, d.am, d.ak, d.ab, d.batch, d.a_kfast != 0, TM, &mapA, &g.a)) return false;
-  if (!plan_operand(d.B, d.bn, d.bk, d.bb, d.batch, d.b_kfast != 0, TN, &mapB, &g.b)) return false;
+  {
+    HostTimer ht(c, 3);
+    if (!plan_operand(d.A, d.am, d.ak, d.ab, d.batch, d.a_kfast != 0, TM, &mapA, &g.a)) return false;
+    if (!plan_operand(d.B, d.bn, d.bk, d.bb, d.batch, d.b_kfast != 0, TN, &mapB, &g.b)) return false;
+  }
   g.M = d.M; g.N = d.N; g.K = d.K; g.batch = d.batch;
   g.cm = d.cm; g.cn = d.cn; g.cb = d.cb;
   g.C = d.C; g.alpha = d.alpha; g.beta = d.beta;
@@ -636,7 +639,10 @@ bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d) {
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = opt_i(c, "TNAD_GEMM_PDL", 1) ? 1 : 0;
-  TNAD_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, g));
+  {
+    HostTimer ht(c, 4);
+    TNAD_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, g));
+  }
   c->launches++;
   TNAD_CUDA(cudaGetLastError());
   return true;

@@ -1,7 +1,18 @@
 // Device tensor plumbing: allocation (stream-ordered pool), views, host<->device staging, timing spans.
 #include "common.h"
+#include <chrono>
 
 namespace tnad {
+
+HostTimer::HostTimer(tnad_ctx* c_, int slot_) : c(c_), slot(slot_), t0(0) {
+  if (c->host_prof) t0 = std::chrono::steady_clock::now().time_since_epoch().count();
+}
+HostTimer::~HostTimer() {
+  if (c->host_prof) {
+    c->hp_ns[slot] += (double)(std::chrono::steady_clock::now().time_since_epoch().count() - t0);
+    c->hp_n[slot]++;
+  }
+}
 
 Tens t_alloc_v(tnad_ctx* c, const std::vector<int64_t>& dims, bool zero) {
   TNAD_REQUIRE((int)dims.size() <= MAXR, "tensor rank too large");
