@@ -230,6 +230,10 @@ TNAD_API int tnad_ctmrg_finish(tnad_ctx* ctx, const double* c1, const double* e1
 TNAD_API int tnad_nccl_unique_id(const char* nccl_path, unsigned char* id128);
 TNAD_API int tnad_comm_init(tnad_ctx* ctx, const char* nccl_path, const unsigned char* id128, int rank, int world);
 TNAD_API int tnad_comm_destroy(tnad_ctx* ctx);
+/* ctmrg + fixedpoint + StopFunction (ctmrg.jl:110-117, fixedpoint.jl:11-41) over the communicator: corner / edge in-out as in
+ * tnad_ctmrg (no tape: forward only) */
+TNAD_API int tnad_ctmrg_sharded(tnad_ctx* ctx, const double* bulk, int D, int chi, double* corner, double* edge, double tol, int maxit,
+                                int* steps_done, double* vals);
 TNAD_API int tnad_ctmrgstep_sharded(tnad_ctx* ctx, const double* bulk, int D, const double* corner, const double* edge, int chi,
                                     double* corner_out, double* edge_out, double* vals, double* ms3);
 

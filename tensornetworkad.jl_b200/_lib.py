@@ -85,6 +85,8 @@ SIGNATURES = {
     "tnad_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "tnad_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "tnad_comm_destroy": (C.c_int, [C.c_void_p]),
+    "tnad_ctmrg_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                                     C.POINTER(C.c_int), c_double_p]),
     "tnad_ctmrgstep_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          c_double_p, c_double_p]),
     "tnad_ctmrg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -537,6 +539,17 @@ class Context:
         self.check(self.lib.tnad_ctmrgstep_sharded(self.h, _p(b), D, _p(co), _p(ed), chi, _p(cn), _p(en),
                                                    vals.ctypes.data_as(c_double_p), ms if timing else None))
         return (cn, en, vals, list(ms)) if timing else (cn, en, vals)
+
+    def ctmrg_sharded(self, bulk, corner, edge, tol, maxit):
+        """ctmrg over the communicator (forward): returns corner, edge, vals, steps."""
+        D, chi = bulk.shape[0], corner.shape[0]
+        b = farray(bulk)
+        co, ed = np.array(corner, dtype=np.float64, order="F", copy=True), np.array(edge, dtype=np.float64, order="F", copy=True)
+        vals = np.empty(chi * D)
+        ns = C.c_int(0)
+        self.check(self.lib.tnad_ctmrg_sharded(self.h, _p(b), D, chi, _p(co), _p(ed), float(tol), int(maxit), C.byref(ns),
+                                               vals.ctypes.data_as(c_double_p)))
+        return co, ed, vals, int(ns.value)
 
     def dev_ctmrgstep_sharded(self, pbulk, D, pcorner, pedge, chi, pcorner_out, pedge_out, timing=True):
         """Device pointers (pointer mode DEVICE must be set by the caller); returns vals (host) and the three device times."""

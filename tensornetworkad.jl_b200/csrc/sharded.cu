@@ -244,6 +244,58 @@ int tnad_comm_destroy(tnad_ctx* c) {
   return TNAD_OK;
 }
 
+// ctmrg(a, chi, tol, maxit) of ctmrg.jl:110-117 / fixedpoint.jl:11-41 over the ranks of the communicator: the stop rule
+// (counter from -1, NaN never converged) runs on every rank on the same replicated spectrum, so all ranks stop together
+int tnad_ctmrg_sharded(tnad_ctx* c, const double* bulk, int D, int chi, double* corner, double* edge, double tol, int maxit,
+                       int* steps_done, double* vals) {
+  if (!c) return TNAD_ERR_ARG;
+  try {
+    TNAD_CUDA(cudaSetDevice(c->device));
+    TNAD_REQUIRE(bulk && corner && edge && D >= 1 && chi >= 1 && maxit >= 0, "tnad_ctmrg_sharded: bad arguments");
+    TNAD_REQUIRE(c->coop_launch, "tnad_ctmrg_sharded: needs cooperative kernel launches");
+    Tens tb = t_in(c, bulk, {D, D, D, D});
+    Tens co = t_clone(c, t_in(c, corner, {chi, chi})), ed = t_clone(c, t_in(c, edge, {chi, D, chi}));
+    const size_t n = (size_t)chi * D;
+    std::vector<double> v(n, INFINITY), old(n, INFINITY);
+    long long counter = -1;   // ctmrg.jl:114
+    int ns = 0;
+    for (;;) {
+      counter += 1;           // fixedpoint.jl:32
+      if (counter > maxit) break;
+      double ss = 0.0;
+      bool isnan = false;
+      for (size_t i = 0; i < n; ++i) {
+        const double d = v[i] - old[i];
+        if (d != d) isnan = true;
+        ss += d * d;
+      }
+      if (!isnan && std::sqrt(ss) <= tol) break;
+      old = v;
+      Tens cn, en;
+      ctmrg_step_sharded(c, tb, co, ed, cn, en, v, nullptr);
+      co = cn;
+      ed = en;
+      ++ns;
+    }
+    t_out(c, co, corner);
+    t_out(c, ed, edge);
+    if (steps_done) *steps_done = ns;
+    if (vals) memcpy(vals, v.data(), n * sizeof(double));
+    sync(c);
+    return TNAD_OK;
+  } catch (const tnad::Error& e) {
+    c->err = e.msg;
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception& e) {
+    c->err = std::string("internal error: ") + e.what();
+    return TNAD_ERR_INTERNAL;
+  } catch (...) {
+    c->err = "unknown internal error";
+    return TNAD_ERR_INTERNAL;
+  }
+}
+
 int tnad_ctmrgstep_sharded(tnad_ctx* c, const double* bulk, int D, const double* corner, const double* edge, int chi,
                            double* corner_out, double* edge_out, double* vals, double* ms3) {
   if (!c) return TNAD_ERR_ARG;

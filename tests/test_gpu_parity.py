@@ -668,6 +668,10 @@ def test_ctmrgstep_sharded_library_entry_single_rank(D, chi):
             assert np.abs(vg - vr).max() < 1e-12
             assert np.abs(cg - cr).max() < 1e-10 and np.abs(eg - er).max() < 1e-10
         assert len(ms) == 3 and ms[2] > 0.0
+        # the fixed-point loop over the same step: same number of steps and spectrum as tnad_ctmrg
+        cl, el, vl, nl = c2.ctmrg_sharded(bulk, c, e, 1e-8, 30)
+        cu, eu, vu, nu = c2.ctmrg(bulk, c, e, 1e-8, 30)
+        assert nl == nu and np.abs(vl - vu).max() < 1e-10 and np.abs(cl - cu).max() < 1e-8
     finally:
         c2.close()
 
