@@ -133,11 +133,11 @@ int tnad_dmma_peak(tnad_ctx* c, double* tflops) {
   TNAD_REQUIRE(tflops, "tnad_dmma_peak: null output");
   Tens sink = t_alloc(c, {4}, true);
   const int iters = 4096, blocks = c->num_sms * 4, warps = 8;
-  k_dmma_peak<<<blocks, 256, 0, c->stream>>>(64, sink.p);   // warm-up
+  for (int wu = 0; wu < 4; ++wu) k_dmma_peak<<<blocks, 256, 0, c->stream>>>(iters, sink.p);   // warm-up: 2 ms of full-rate DMMA (the probe was bimodal, 29.7 / 37.0 TFLOP/s, with a 64-iteration warm-up)
   TNAD_CUDA(cudaGetLastError());
   cudaEvent_t a = get_event(c), b = get_event(c);
   double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
+  for (int rep = 0; rep < 10; ++rep) {
     TNAD_CUDA(cudaEventRecord(a, c->stream));
     k_dmma_peak<<<blocks, 256, 0, c->stream>>>(iters, sink.p);
     TNAD_CUDA(cudaEventRecord(b, c->stream));
@@ -149,7 +149,7 @@ int tnad_dmma_peak(tnad_ctx* c, double* tflops) {
   }
   c->event_pool.push_back(a);
   c->event_pool.push_back(b);
-  c->launches += 6;
+  c->launches += 14;
   *tflops = best;
   API_END(c)
 }
