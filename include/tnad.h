@@ -128,6 +128,10 @@ TNAD_API int tnad_tape_free(tnad_tape* tape);
 /* ---- CTMRG (ctmrg.jl:66-153, fixedpoint.jl:11-41) ---------------------------------------- */
 /* _initializect_square(bulk, Val(:raw), chi)  (ctmrg.jl:74-86) */
 TNAD_API int tnad_ctmrg_init_raw(tnad_ctx* ctx, const double* bulk, int D, int chi, double* corner, double* edge);
+/* _initializect_square(bulk, Val(:random), chi)  (ctmrg.jl:66-72) generated on the device: randn from a counter-based generator
+ * (reproducible from `seed`; the reference uses Julia's global RNG, whose stream cannot be matched), corner += corner',
+ * edge += permutedims(edge, (3,2,1)) */
+TNAD_API int tnad_ctmrg_init_random(tnad_ctx* ctx, int D, int chi, unsigned long long seed, double* corner, double* edge);
 /* one ctmrgstep (ctmrg.jl:126-153): bulk D^4, corner chi^2, edge chi*D*chi; vals has chi*D entries */
 TNAD_API int tnad_ctmrgstep(tnad_ctx* ctx, const double* bulk, int D, int chi,
                    const double* corner_in, const double* edge_in,

@@ -49,6 +49,7 @@ SIGNATURES = {
                                    c_double_p, C.POINTER(C.c_void_p)]),
     "tnad_trg_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "tnad_tape_free": (C.c_int, [C.c_void_p]),
+    "tnad_ctmrg_init_random": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]),
     "tnad_ctmrg_init_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tnad_ctmrgstep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, c_double_p]),
@@ -352,6 +353,12 @@ class Context:
         D = bulk.shape[0]
         corner = np.empty((chi, chi), order="F"); edge = np.empty((chi, D, chi), order="F")
         self.check(self.lib.tnad_ctmrg_init_raw(self.h, _p(bulk), D, int(chi), _p(corner), _p(edge)))
+        return corner, edge
+
+    def ctmrg_init_random(self, D, chi, seed):
+        """:random environment generated on the device (reproducible from the seed)."""
+        corner = np.empty((chi, chi), order="F"); edge = np.empty((chi, D, chi), order="F")
+        self.check(self.lib.tnad_ctmrg_init_random(self.h, int(D), int(chi), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(corner), _p(edge)))
         return corner, edge
 
     def ctmrgstep(self, bulk, corner, edge):

@@ -495,6 +495,16 @@ int tnad_ctmrg_init_raw(tnad_ctx* c, const double* bulk, int D, int chi, double*
   TNAD_API_END(c)
 }
 
+int tnad_ctmrg_init_random(tnad_ctx* c, int D, int chi, unsigned long long seed, double* corner, double* edge) {
+  TNAD_API_BEGIN(c)
+  TNAD_REQUIRE(D >= 1 && chi >= 1 && corner && edge, "tnad_ctmrg_init_random: bad arguments");
+  Tens co, ed;
+  init_random(c, D, chi, seed, co, ed);
+  t_out(c, co, corner);
+  t_out(c, ed, edge);
+  TNAD_API_END(c)
+}
+
 int tnad_ctmrgstep(tnad_ctx* c, const double* bulk, int D, int chi, const double* corner_in, const double* edge_in,
                    double* corner_out, double* edge_out, double* vals) {
   TNAD_API_BEGIN(c)

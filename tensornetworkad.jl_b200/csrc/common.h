@@ -264,6 +264,7 @@ void colscale_sqrt(tnad_ctx* c, const double* in, int64_t ldin, const double* S,
                    int64_t m, int64_t k);
 void set_identity(tnad_ctx* c, double* p, int64_t ld, int64_t n);
 void init_raw(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge);
+void init_random(tnad_ctx* c, int64_t D, int64_t chi, unsigned long long seed, Tens& corner, Tens& edge);
 void ipeps_symmetrize(tnad_ctx* c, const Tens& A, Tens& xsum, Tens& out, double* ss);
 void ipeps_symmetrize_back(tnad_ctx* c, const Tens& ybar, const Tens& xsum, const double* ss, Tens& Abar);
 void double_layer(tnad_ctx* c, const Tens& A, Tens& ap, Tens& a);

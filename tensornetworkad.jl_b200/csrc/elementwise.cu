@@ -483,6 +483,38 @@ void init_raw(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge) {
   LAUNCH_CHECK(c);
 }
 
+// _initializect_square(bulk, Val(:random), chi) (ctmrg.jl:66-72) on the device: standard normals from a counter-based
+// generator (splitmix64 of (seed, element index) -> two uniforms -> Box-Muller), then corner += corner', edge +=
+// permutedims(edge, (3,2,1)).  The reference draws from Julia's global RNG, so the stream cannot be matched anyway; what
+// the caller gets is the same distribution, reproducible from the seed and independent of the launch geometry.
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void k_randn(double* __restrict__ out, long long n, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long a = splitmix64(seed ^ splitmix64(2ull * (unsigned long long)i));
+    const unsigned long long b = splitmix64(seed ^ splitmix64(2ull * (unsigned long long)i + 1ull));
+    const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);      // (0, 1]
+    const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);              // [0, 1)
+    out[i] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  }
+}
+
+void init_random(tnad_ctx* c, int64_t D, int64_t chi, unsigned long long seed, Tens& corner, Tens& edge) {
+  Tens c0 = t_alloc(c, {chi, chi}), e0 = t_alloc(c, {chi, D, chi});
+  k_randn<<<grid_for(c0.numel()), TB, 0, c->stream>>>(c0.p, c0.numel(), splitmix64(seed));
+  LAUNCH_CHECK(c);
+  k_randn<<<grid_for(e0.numel()), TB, 0, c->stream>>>(e0.p, e0.numel(), splitmix64(seed + 0x5851F42D4C957F2Dull));
+  LAUNCH_CHECK(c);
+  corner = t_clone(c, c0);
+  edge = t_clone(c, e0);
+  tcopy(c, t_perm(c0, {1, 0}), corner, 1.0, 1.0);
+  tcopy(c, t_perm(e0, {2, 1, 0}), edge, 1.0, 1.0);
+}
+
 // indexperm_symmetrize (ipeps.jl:32-39): four permute-adds, then x / norm(x)
 static const int SYM_PERMS[4][5] = {{0, 3, 2, 1, 4}, {2, 1, 0, 3, 4}, {1, 0, 3, 2, 4}, {3, 2, 1, 0, 4}};
 

@@ -376,6 +376,23 @@ def test_magnetisation_gradient(ctx):
         assert y == pytest.approx(yo, rel=1e-10, abs=1e-12) and g == pytest.approx(go, rel=1e-7, abs=1e-10)
 
 
+def test_init_random_on_device(ctx):
+    # ctmrg.jl:66-72: randn + symmetrisation; reproducible from the seed, different seeds differ, moments of N(0, 2) / N(0, 4)
+    c, e = ctx.ctmrg_init_random(4, 96, 7)
+    c2, e2 = ctx.ctmrg_init_random(4, 96, 7)
+    c3, _ = ctx.ctmrg_init_random(4, 96, 8)
+    assert np.array_equal(c, c2) and np.array_equal(e, e2) and not np.array_equal(c, c3)
+    assert np.array_equal(c, c.T) and np.array_equal(e, np.transpose(e, (2, 1, 0)))
+    off = e[np.triu_indices(96, 1)[0], :, np.triu_indices(96, 1)[1]]        # x_ij + x_ji, i != j: variance 2
+    assert abs(off.mean()) < 0.02 and abs(off.var() - 2.0) < 0.05
+    assert abs(np.diag(c).var() - 4.0) < 1.5 and np.isfinite(e).all()
+    # and it is a usable start: CTMRG Ising converges to the Onsager magnetisation from it
+    a, m = T.model_tensor(T.Ising(), 0.5), T.mag_tensor(T.Ising(), 0.5)
+    c0, e0 = ctx.ctmrg_init_random(2, 16, 3)
+    cc, ee, vals, steps = ctx.ctmrg(a, c0, e0, 1e-10, 500)
+    assert abs(abs(ctx.magnetisation_readout(a, m, cc, ee)) - T.magofbeta(T.Ising(), 0.5)) < 1e-6
+
+
 def test_magnetisation_readout_backward_vs_oracle(ctx):
     rng = np.random.default_rng(4)
     a, m = O.model_tensor_ising(0.45), O.mag_tensor_ising(0.45)
