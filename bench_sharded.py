@@ -151,11 +151,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--impl", default="library", choices=["library", "python"])
+    ap.add_argument("--check-energy", action="store_true",
+                    help="energy + gradient (d=2, chi=32, maxit=4) on the communicator context (sharded forward steps, replicated "
+                         "reverse sweep) against a plain context on every rank")
     args = ap.parse_args()
     import tnad_b200 as T
     dist = Dist()
     ctx = T.Context(dist.local_rank)
     r = measure(dist, ctx, args.d, args.chi, args.steps, args.warmup, args.check, args.impl)
+    if args.check_energy:
+        comm_setup(dist, ctx)
+        h = T.hamiltonian(T.Heisenberg())
+        A = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(3).standard_normal((2, 2, 2, 2, 2)))).bulk
+        e1, g1 = ctx.energy(h, A, 32, 0.0, 4, grad=True)
+        plain = T.Context(dist.local_rank)
+        e0, g0 = plain.energy(h, A, 32, 0.0, 4, grad=True)
+        plain.close()
+        r["check_energy_rel_diff"] = dist.max(abs(e1 - e0) / abs(e0))
+        r["check_gradient_rel_diff"] = dist.max(float(np.abs(g1 - g0).max() / np.abs(g0).max()))
     if dist.rank == 0:
         print(json.dumps({
             "metric": "sharded_ctmrgstep_seconds", "value": r["s_per_step"], "unit": "s/step", "n_gpus": dist.world,
@@ -164,6 +177,7 @@ def main():
             "ms_contract": r["ms_contract"], "ms_gather": r["ms_gather"], "ms_svd": r["ms_svd"],
             "gather_bytes_per_step": r["gather_bytes_per_step"],
             "check_max_abs_diff_vs_unsharded": r["check_max_abs_diff_vs_unsharded"],
+            "check_energy_rel_diff": r.get("check_energy_rel_diff"), "check_gradient_rel_diff": r.get("check_gradient_rel_diff"),
         }), flush=True)
     dist.barrier()
     ctx.close()

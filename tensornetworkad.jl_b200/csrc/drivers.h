@@ -81,8 +81,10 @@ void magnetisation_readout_back(tnad_ctx* c, const Tens& a, const Tens& m, const
                                 const MagTape& t, double ybar, Tens& abar, Tens& mbar, Tens& cornerbar, Tens& edgebar);
 
 // chi-sharded ctmrgstep over the ranks of the context's communicator (sharded.cu)
+// rec (optional): the record ctmrg_step_backward needs, so that the unrolled reverse sweep (replicated on every rank) can follow
+// a forward pass whose steps were sharded
 void ctmrg_step_sharded(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& edge, Tens& corner_out, Tens& edge_out,
-                        std::vector<double>& vals_host, double* ms);
+                        std::vector<double>& vals_host, double* ms, CtmrgStepRec* rec = nullptr);
 
 }  // namespace tnad
 

@@ -80,7 +80,7 @@ void all_gather(tnad_ctx* c, const double* send, double* recv, size_t count) {
 // One ctmrgstep with the contractions and the back-transformation of the eigen-decomposition shared between the ranks of
 // the context's communicator.  ms (optional, 3 doubles): device time of contractions (+ finish), all-gathers, decomposition.
 void ctmrg_step_sharded(tnad_ctx* c, const Tens& bulk, const Tens& corner, const Tens& edge, Tens& corner_out, Tens& edge_out,
-                        std::vector<double>& vals_host, double* ms) {
+                        std::vector<double>& vals_host, double* ms, CtmrgStepRec* rec) {
   const int world = c->comm_world > 1 ? c->comm_world : 1, rank = c->comm_world > 1 ? c->comm_rank : 0;
   const int64_t D = bulk.dim[0], chi = corner.dim[0], n = chi * D;
   TNAD_REQUIRE(chi % world == 0, "tnad_ctmrgstep_sharded: chi must be divisible by the number of ranks");
@@ -105,6 +105,11 @@ void ctmrg_step_sharded(tnad_ctx* c, const Tens& bulk, const Tens& corner, const
   mark();                                                                       // 1
   all_gather(c, cpk_r.p, cpk.p, (size_t)(chi * D * D * w));
   mark();                                                                       // 2
+  Tens X2full;
+  if (rec) {   // the reverse sweep wants the full X2[i,b,c,l]: the slices concatenate along l
+    X2full = t_alloc(c, {chi, D, D, chi});
+    all_gather(c, X2r.p, X2full.p, (size_t)(chi * D * D * w));
+  }
   Tens cp = t_alloc(c, {chi, D, chi, D});
   tcopy(c, t_perm(cpk, {0, 1, 3, 2}), cp);
   Tens CP = t_reshape(cp, {n, n});
@@ -167,6 +172,21 @@ void ctmrg_step_sharded(tnad_ctx* c, const Tens& bulk, const Tens& corner, const
   vals_host.resize((size_t)n);
   const double s0 = svd.s_host[0];
   for (int64_t i = 0; i < n; ++i) vals_host[i] = svd.s_host[i] / s0;            // ctmrg.jl:142
+  if (rec) {
+    // record for ctmrg_step_backward (replicated on every rank): it uses the intermediates of the unsharded association
+    // Y1 = z edge, Y2 = Y1 bulk, recomputed here in full (2 of the step's 8 products; the decomposition dominates)
+    rec->corner = corner;
+    rec->edge = edge;
+    rec->X1 = X1;
+    rec->X2 = X2full;
+    rec->cp = cp;
+    rec->svd = svd;
+    rec->Y1 = contract_new(c, "abi,aed->ibed", zall, edge);
+    rec->Y2 = contract_new(c, "ibed,bjce->ijcd", rec->Y1, bulk);
+    rec->c2 = c2;
+    rec->e2 = e2;
+    rec->ss = ss;
+  }
   if (ms) {
     TNAD_CUDA(cudaEventSynchronize(ev[7]));
     float t[7];
@@ -272,7 +292,7 @@ int tnad_ctmrg_sharded(tnad_ctx* c, const double* bulk, int D, int chi, double* 
       if (!isnan && std::sqrt(ss) <= tol) break;
       old = v;
       Tens cn, en;
-      ctmrg_step_sharded(c, tb, co, ed, cn, en, v, nullptr);
+      ctmrg_step_sharded(c, tb, co, ed, cn, en, v, nullptr, nullptr);
       co = cn;
       ed = en;
       ++ns;
@@ -306,7 +326,7 @@ int tnad_ctmrgstep_sharded(tnad_ctx* c, const double* bulk, int D, const double*
     Tens tb = t_in(c, bulk, {D, D, D, D}), tc = t_in(c, corner, {chi, chi}), te = t_in(c, edge, {chi, D, chi});
     Tens co, eo;
     std::vector<double> v;
-    ctmrg_step_sharded(c, tb, tc, te, co, eo, v, ms3);
+    ctmrg_step_sharded(c, tb, tc, te, co, eo, v, ms3, nullptr);
     t_out(c, co, corner_out);
     t_out(c, eo, edge_out);
     if (vals) memcpy(vals, v.data(), v.size() * sizeof(double));   // the spectrum is host data in both pointer modes (as in tnad_ctmrgstep)

@@ -694,6 +694,24 @@ def test_ctmrgstep_sharded_library_entry_single_rank(D, chi):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("chi,maxit", [(8, 5), (40, 3), (160, 2)])
+def test_energy_and_gradient_through_the_sharded_loop(ctx, chi, maxit):
+    """A context that joined a communicator runs its CTMRG steps through ctmrg_step_sharded and records them for the
+    unrolled reverse sweep: energy and gradient must equal those of a plain context (world 1 here; 2+ GPUs:
+    bench_sharded.py --check-energy)."""
+    h = T.hamiltonian(T.Heisenberg())
+    A = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(chi).standard_normal((2, 2, 2, 2, 2)))).bulk
+    e0, g0 = ctx.energy(h, A, chi, 0.0, maxit, grad=True)
+    c2 = T.Context(0)
+    try:
+        c2.comm_init(None, 0, 1)
+        e1, g1 = c2.energy(h, A, chi, 0.0, maxit, grad=True)
+    finally:
+        c2.close()
+    assert abs(e1 - e0) <= 1e-12 * abs(e0) and np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+
+
+@pytest.mark.gpu
 def test_permute_and_svd_symmetrized_device_pointers(ctx):
     import torch
     rng = np.random.default_rng(3)
