@@ -94,6 +94,7 @@ struct tnad_ctx {
   bool host_prof = false;
   double hp_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long hp_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemPool_t side_pool = nullptr;   // allocations made while c->stream == stream2 (side-stream work)
   int gemm_grid_cap = 0;       // > 0: persistent GEMM grids use at most this many CTAs (side-stream work next to a kernel that owns SMs)
   int64_t gemm_tma_n = 0, gemm_fallback_n = 0;   // products on the TMA kernel / on the cp.async kernel
   double gemm_flops = 0.0, gemm_tma_flops = 0.0; // 2 M N K batch of the products launched while kernel timing is on
@@ -141,7 +142,10 @@ struct DBuf {
   size_t n;
   DBuf(tnad_ctx* c_, size_t n_) : c(c_), p(nullptr), n(n_) {
     HostTimer ht(c, 1);
-    TNAD_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(double), c->stream));
+    if (c->side_pool && c->stream == c->stream2)
+      TNAD_CUDA(cudaMallocFromPoolAsync((void**)&p, (n ? n : 1) * sizeof(double), c->side_pool, c->stream));
+    else
+      TNAD_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(double), c->stream));
   }
   ~DBuf() {
     HostTimer ht(c, 2);

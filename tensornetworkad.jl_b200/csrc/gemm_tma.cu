@@ -30,8 +30,8 @@ namespace tnad {
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16;
-constexpr int NSTAGE = 6;                      // stages per consumer group
-constexpr int NGRP = 2;                        // consumer groups per CTA, one producer warp each
+constexpr int NSTAGE = 4;                      // stages per consumer group
+constexpr int NGRP = 3;                        // consumer groups per CTA, one producer warp each
 constexpr int NCONS = 4;                       // consumer warps per group (2 x 2 warp tiles of 32 x 32)
 constexpr int NTHREADS = 32 * NGRP * (NCONS + 1);
 constexpr int TILE_BYTES = TM * TK * 8;        // one operand tile of one stage
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const unsigned sbase = (sbase0 + 1023u) & ~1023u;
   unsigned char* sgen = smem_raw + (sbase - sbase0);
   const unsigned bars = sbase + NGRP * NSTAGE * 2 * TILE_BYTES;   // per group: full[NSTAGE], empty[NSTAGE]; then the stagger barrier
-  const unsigned stag = bars + 8 * NGRP * 2 * NSTAGE;
+  const unsigned stag = bars + 8 * NGRP * 2 * NSTAGE;           // NGRP - 1 stagger barriers: group g + 1 waits for group g
   __shared__ int s_last[NGRP];
   __shared__ long long s_off[NGRP][TM + TN];
 
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         mbar_init(bars + 8 * (q * 2 * NSTAGE + s), 1);
         mbar_init(bars + 8 * (q * 2 * NSTAGE + NSTAGE + s), NCONS);
       }
-    mbar_init(stag, NCONS);
+    for (int q = 0; q + 1 < NGRP; ++q) mbar_init(stag + 8 * q, NCONS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   bool first = true;
   for (int u = u0; u < g.units; u += ustep) {
     const Unit un = unit_of(g, u);
-    if (first && grp == 1 && !mbar_wait(stag, 0)) __trap();        // half a tile behind group 0
+    if (first && grp >= 1 && !mbar_wait(stag + 8 * (grp - 1), 0)) __trap();   // 1 / NGRP of a tile behind the group before
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(empty0 + 8 * s);
-        if (first && grp == 0 && kt == un.nkt / 2) mbar_arrive(stag);
+        if (first && grp + 1 < NGRP && kt == un.nkt / NGRP) mbar_arrive(stag + 8 * grp);
       }
     }
     first = false;
@@ -617,7 +617,7 @@ bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d) {
   g.tn = (int)tn;
   g.units = (int)(tiles * S);
   g.dbg_nofetch = opt_i(c, "TNAD_GEMM_NOFETCH", 0);
-  const size_t smem = (size_t)NGRP * NSTAGE * 2 * TILE_BYTES + (NGRP * 2 * NSTAGE + 1) * 8 + 1024;
+  const size_t smem = (size_t)NGRP * NSTAGE * 2 * TILE_BYTES + (NGRP * 2 * NSTAGE + NGRP) * 8 + 1024;
   void (*kern)(CUtensorMap, CUtensorMap, TmaGemm) =
       g.a.kfast ? (g.b.kfast ? gemm_tma_kernel<true, true> : gemm_tma_kernel<true, false>)
                 : (g.b.kfast ? gemm_tma_kernel<false, true> : gemm_tma_kernel<false, false>);
