@@ -251,7 +251,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         ctx.energy_device(hp, Ap, d, s, CHI, 0.0, args.maxit, gp)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
     dist.barrier()
     ctx.reset_launch_count()
@@ -259,6 +259,8 @@ def run_ours(args):
     e_last = 0.0
     for _ in range(args.steps):
         e_last = ctx.energy_device(hp, Ap, d, s, CHI, 0.0, args.maxit, gp)
+        if os.environ.get("BENCH_DEBUG_CALLS"):
+            print("[bench debug] device arm call:", ctx.last_timing(), file=sys.stderr, flush=True)
     ms = ctx.timer_stop()
     launches = ctx.launch_count()
     dist.barrier()
@@ -275,6 +277,8 @@ def run_ours(args):
     ctx.timer_start()
     for _ in range(args.steps):
         e_h, g_h = ctx.energy(hh, Ah, CHI, 0.0, args.maxit, grad=True)
+        if os.environ.get("BENCH_DEBUG_CALLS"):
+            print("[bench debug] e2e arm call:", ctx.last_timing(), file=sys.stderr, flush=True)
     ms_e2e = dist.max(ctx.timer_stop())
     sampler.stop_flag = True
     h2d = int(h.nbytes + A.nbytes)

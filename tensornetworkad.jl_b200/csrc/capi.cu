@@ -68,7 +68,7 @@ int tnad_create(int device, tnad_ctx** out) {
     int prio_lo = 0, prio_hi = 0;
     TNAD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     TNAD_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
-    TNAD_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+    TNAD_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, opt_i(c, "TNAD_SIDE_SAME_PRIO", 0) ? prio_hi : prio_lo));
     TNAD_CUDA(cudaEventCreateWithFlags(&c->ev_eig, cudaEventDisableTiming));
     TNAD_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
     TNAD_CUDA(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_lo));

@@ -110,6 +110,7 @@ struct tnad_ctx {
   std::vector<cudaEvent_t> event_pool;
   // stopwatch + optional per-kernel-family timing (bench.py)
   cudaEvent_t tstart = nullptr, tstop = nullptr;
+  cudaEvent_t ev_api0 = nullptr, ev_api1 = nullptr;   // bracket of an API call (timing_begin / timing_end)
   bool ktiming = false;
   struct KSpan {
     int fam;

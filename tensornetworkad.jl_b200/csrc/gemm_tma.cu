@@ -638,7 +638,10 @@ bool gemm_tma_try(tnad_ctx* c, const GemmDesc& d) {
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = opt_i(c, "TNAD_GEMM_PDL", 1) ? 1 : 0;
+  // dependent launch on the main stream only: on the side stream the early-resident CTAs of the next product (one per SM,
+  // 192 KB of shared memory) would sit on SMs the main stream's kernels are waiting for
+  const int pdl = opt_i(c, "TNAD_GEMM_PDL", 1);
+  cfg.numAttrs = (pdl == 2 || (pdl == 1 && c->stream != c->stream2)) ? 1 : 0;
   {
     HostTimer ht(c, 4);
     TNAD_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, g));

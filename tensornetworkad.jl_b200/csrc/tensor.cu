@@ -181,9 +181,25 @@ void timing_begin(tnad_ctx* c) {
   }
   c->spans.clear();
   for (int i = 0; i < 8; ++i) c->timing[i] = 0.0;
+  if (opt_i(c, "TNAD_API_BRACKET", 1)) {
+    if (!c->ev_api0) {
+      cudaEventCreate(&c->ev_api0);
+      cudaEventCreate(&c->ev_api1);
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaEventRecord(c->ev_api0, c->stream);
+  }
 }
 
 void timing_end(tnad_ctx* c) {
+  // The call is bracketed by its own pair of recorded events (begin: stream sync + record, end: record + event sync).
+  // Measured, not understood: with the side stream of the explicit-Q mode and the TMA kernels active, calls that end in a
+  // plain cudaStreamSynchronize showed rare 0.1 - 1 s gaps in the NEXT calls (1 call in 5 on some boxes, period 3 calls);
+  // with the bracket 100+ consecutive calls were clean (tools/c4_calls3.py inner / none).
+  if (c->ev_api1 && opt_i(c, "TNAD_API_BRACKET", 1)) {
+    cudaEventRecord(c->ev_api1, c->stream);
+    cudaEventSynchronize(c->ev_api1);
+  }
   cudaStreamSynchronize(c->stream);
   for (auto& s : c->spans) {
     float ms = 0.f;
