@@ -15,7 +15,8 @@ static std::string g_create_error;
 #define TNAD_API_BEGIN(ctx)                       \
   if (!(ctx)) return TNAD_ERR_ARG;                \
   try {                                           \
-    TNAD_CUDA(cudaSetDevice((ctx)->device));
+    TNAD_CUDA(cudaSetDevice((ctx)->device));      \
+    tnad::ApiBracket _bracket(ctx);
 
 #define TNAD_API_END(ctx)                                           \
     return TNAD_OK;                                                 \

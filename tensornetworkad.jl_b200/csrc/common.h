@@ -196,6 +196,13 @@ void sync(tnad_ctx* c);
 void d2h(tnad_ctx* c, double* host, const double* dev, size_t n);               // synchronous
 void h2d(tnad_ctx* c, double* dev, const double* host, size_t n);
 
+// Every C-ABI call that enqueues work is bracketed by its own pair of recorded events (see timing_end in tensor.cu)
+struct ApiBracket {
+  tnad_ctx* c;
+  explicit ApiBracket(tnad_ctx* c);
+  ~ApiBracket();
+};
+
 // timing spans (CUDA events on the ctx stream)
 struct Span {
   tnad_ctx* c;

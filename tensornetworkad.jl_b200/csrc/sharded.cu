@@ -271,6 +271,7 @@ int tnad_ctmrg_sharded(tnad_ctx* c, const double* bulk, int D, int chi, double* 
   if (!c) return TNAD_ERR_ARG;
   try {
     TNAD_CUDA(cudaSetDevice(c->device));
+    tnad::ApiBracket _bracket(c);
     TNAD_REQUIRE(bulk && corner && edge && D >= 1 && chi >= 1 && maxit >= 0, "tnad_ctmrg_sharded: bad arguments");
     TNAD_REQUIRE(c->coop_launch, "tnad_ctmrg_sharded: needs cooperative kernel launches");
     Tens tb = t_in(c, bulk, {D, D, D, D});
@@ -321,6 +322,7 @@ int tnad_ctmrgstep_sharded(tnad_ctx* c, const double* bulk, int D, const double*
   if (!c) return TNAD_ERR_ARG;
   try {
     TNAD_CUDA(cudaSetDevice(c->device));
+    tnad::ApiBracket _bracket(c);
     TNAD_REQUIRE(bulk && corner && edge && corner_out && edge_out && D >= 1 && chi >= 1, "tnad_ctmrgstep_sharded: bad arguments");
     TNAD_REQUIRE(c->coop_launch, "tnad_ctmrgstep_sharded: needs cooperative kernel launches");
     Tens tb = t_in(c, bulk, {D, D, D, D}), tc = t_in(c, corner, {chi, chi}), te = t_in(c, edge, {chi, D, chi});

@@ -174,6 +174,24 @@ Span::~Span() {
   c->spans.push_back({key, {a, b}});
 }
 
+ApiBracket::ApiBracket(tnad_ctx* c_) : c(c_) {
+  if (!opt_i(c, "TNAD_API_BRACKET", 1)) {
+    c = nullptr;
+    return;
+  }
+  if (!c->ev_api0) {
+    cudaEventCreate(&c->ev_api0);
+    cudaEventCreate(&c->ev_api1);
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaEventRecord(c->ev_api0, c->stream);
+}
+ApiBracket::~ApiBracket() {
+  if (!c) return;
+  cudaEventRecord(c->ev_api1, c->stream);
+  cudaEventSynchronize(c->ev_api1);
+}
+
 void timing_begin(tnad_ctx* c) {
   for (auto& s : c->spans) {
     c->event_pool.push_back(s.second.first);
