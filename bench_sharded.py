@@ -163,7 +163,9 @@ def main():
         comm_setup(dist, ctx)
         h = T.hamiltonian(T.Heisenberg())
         A = T.indexperm_symmetrize(T.SquareIPEPS(np.random.default_rng(3).standard_normal((2, 2, 2, 2, 2)))).bulk
+        ctx.set_option("TNAD_SHARDED_LOOP", "1")        # collective from here on: every rank makes the same calls
         e1, g1 = ctx.energy(h, A, 32, 0.0, 4, grad=True)
+        ctx.set_option("TNAD_SHARDED_LOOP", None)
         plain = T.Context(dist.local_rank)
         e0, g0 = plain.energy(h, A, 32, 0.0, 4, grad=True)
         plain.close()

@@ -231,9 +231,10 @@ TNAD_API int tnad_ctmrg_finish(tnad_ctx* ctx, const double* c1, const double* e1
  * library makes the sharded entry point run on one GPU.  tnad_ctmrgstep_sharded: every rank passes the same bulk / corner /
  * edge (pointer mode applies; chi divisible by the number of ranks) and receives the full corner_out / edge_out; vals (chi*D,
  * host) and ms3 (host, optional: device ms of contractions, all-gathers, eigen-decomposition) as in tnad_ctmrgstep.
- * After tnad_comm_init the fixed-point loops of this context (tnad_ctmrg, tnad_energy, tnad_energy_fixedpoint) run their steps
- * through the sharded step as well and record them in full, so tapes and gradients work unchanged: the forward pass is shared
- * between the ranks, the reverse sweep is replicated (option TNAD_SHARDED_LOOP = 0 switches that off). */
+ * Opt-in (tnad_set_option(ctx, "TNAD_SHARDED_LOOP", "1") after tnad_comm_init): the fixed-point loops of this context
+ * (tnad_ctmrg, tnad_energy, tnad_energy_fixedpoint) run their steps through the sharded step as well and record them in full, so
+ * tapes and gradients work unchanged: the forward pass is shared between the ranks, the reverse sweep is replicated.  Those calls
+ * are then COLLECTIVE: every rank of the communicator must make them. */
 TNAD_API int tnad_nccl_unique_id(const char* nccl_path, unsigned char* id128);
 TNAD_API int tnad_comm_init(tnad_ctx* ctx, const char* nccl_path, const unsigned char* id128, int rank, int world);
 TNAD_API int tnad_comm_destroy(tnad_ctx* ctx);

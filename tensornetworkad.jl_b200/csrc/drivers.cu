@@ -333,9 +333,11 @@ int ctmrg_loop(tnad_ctx* c, const Tens& bulk, Tens& corner, Tens& edge, double t
     oldvals = vals;
     Tens cn, en;
     CtmrgStepRec rec;
-    // a context that joined a communicator (tnad_comm_init) runs its CTMRG steps chi-sharded over the ranks; every rank keeps
-    // the full record, so tnad_ctmrg_backward / tnad_energy work unchanged (forward shared, reverse sweep replicated)
-    if (c->comm_world >= 1 && opt_i(c, "TNAD_SHARDED_LOOP", 1) != 0 && corner.dim[0] % c->comm_world == 0)
+    // OPT-IN (option TNAD_SHARDED_LOOP = 1 on a context that joined a communicator): the CTMRG steps run chi-sharded over the
+    // ranks and every rank keeps the full record, so tnad_ctmrg_backward / tnad_energy work unchanged (forward shared, reverse
+    // sweep replicated).  Off by default: the call becomes COLLECTIVE -- every rank of the communicator must make it, a rank
+    // that calls tnad_energy on its own would wait in ncclAllGather for ever.
+    if (c->comm_world >= 1 && opt_i(c, "TNAD_SHARDED_LOOP", 0) != 0 && corner.dim[0] % c->comm_world == 0)
       ctmrg_step_sharded(c, bulk, corner, edge, cn, en, vals, nullptr, tape ? &rec : nullptr);
     else
       ctmrg_step(c, bulk, corner, edge, cn, en, vals, tape ? &rec : nullptr, warm ? &Vwarm : nullptr);

@@ -705,6 +705,7 @@ def test_energy_and_gradient_through_the_sharded_loop(ctx, chi, maxit):
     c2 = T.Context(0)
     try:
         c2.comm_init(None, 0, 1)
+        c2.set_option("TNAD_SHARDED_LOOP", "1")      # opt-in: the call is collective over the communicator
         e1, g1 = c2.energy(h, A, chi, 0.0, maxit, grad=True)
     finally:
         c2.close()
