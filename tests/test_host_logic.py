@@ -360,9 +360,10 @@ def test_one_barrier_tridiagonalisation_prototype(kind):
 
 
 # ---- bench.py contract: the committed result line carries every key the driver reads -------------------------------
-def test_recorded_bench_line_has_contract_keys():
+@pytest.mark.parametrize("name", ["r1_bench_n1.json", "r2_bench_n1.json"])
+def test_recorded_bench_line_has_contract_keys(name):
     import json
-    path = os.path.join(ROOT, "profiles", "r1_bench_n1.json")
+    path = os.path.join(ROOT, "profiles", name)
     line = json.loads(open(path).read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
@@ -377,6 +378,19 @@ def test_recorded_bench_line_has_contract_keys():
     c = line["cpu_baseline"]
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("port", "reference")
     assert line["gpu_launches"] > 0 and line["clocks"]["reasons"] == []
+    if name.startswith("r2"):     # round 2: same-config CPU sample checked against the GPU in the run, whole metric in the line
+        assert line["parity_check"]["ok"] is True and line["contractions"]["frac_of_dmma_peak"] > 0.5
+        assert line["trg_chi64_iters_per_s"] > 1.8 and line["trg_chi64"]["parity_vs_oracle_fixture"]["lnZ_rel_err"] < 1e-10
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_recorded_multi_gpu_lines(n):
+    import json
+    line = json.loads(open(os.path.join(ROOT, "profiles", f"r2_bench_n{n}.json")).read().strip().splitlines()[-1])
+    assert line["n_gpus"] == n and line["scaling"] == "weak" and line["value"] > 0
+    assert line["sweep_instances_per_s"] > 0 and line["sharded_s_per_step"] > 0
+    for k in ("sharded_ms_contract", "sharded_ms_gather", "sharded_ms_svd"):
+        assert line[k] >= 0
 
 
 def test_golub_kahan_prototype():
