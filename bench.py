@@ -99,7 +99,6 @@ class Dist:
             import torch
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
-            os.environ.setdefault("NCCL_DEBUG", "WARN")      # no version banner on stdout: rank 0 prints exactly one JSON line
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
             dist.init_process_group(backend=backend)
