@@ -393,6 +393,28 @@ def test_recorded_multi_gpu_lines(n):
         assert line[k] >= 0
 
 
+def test_tma_shared_memory_layout_prototype():
+    """The fragment addressing of gemm_tma.cu (128-byte swizzle, k permutation, lane -> row assignment): every lane gets
+    exactly A[row(blk, gq), k(kk, t)] from both tile layouts, and every 128-bit load is conflict-free per quarter warp."""
+    P = _load_tool("tma_layout_proto")
+    rng = np.random.default_rng(5)
+    tile = rng.standard_normal((64, 16))
+    assert sorted(P.kmap(kk, t) for kk in range(4) for t in range(4)) == list(range(16))      # a bijection onto the k-tile
+    for kfast in (True, False):
+        img = P.tile_image(tile, kfast)
+        assert not np.isnan(img).any()                                                        # the layout fills the stage exactly
+        for w0 in (0, 32):
+            frag, loads = P.warp_fragments(img, kfast, w0)
+            for blk in range(4):
+                for kk in range(4):
+                    for lane in range(32):
+                        gq, t = lane >> 2, lane & 3
+                        assert frag[blk, kk, lane] == tile[P.rowmap(kfast, w0, blk, gq), P.kmap(kk, t)]
+            assert len(loads) == 8 and all(P.wavefronts_128(a) == 4 for a in loads)          # 4 = the minimum for 512 bytes
+            rows = sorted(P.rowmap(kfast, w0, blk, gq) for blk in range(4) for gq in range(8))
+            assert rows == list(range(w0, w0 + 32))                                           # the warp tile is covered once
+
+
 def test_golub_kahan_prototype():
     P = _load_tool("gebrd_proto")
     rng = np.random.default_rng(3)
