@@ -10,9 +10,9 @@
 //     row-fast) need the minimum of two wavefronts;
 //   * one producer warp (one elected lane issues the boxes and arms the `full` mbarrier of the stage with the byte count),
 //     four consumer warps (32 x 32 warp tiles, accumulators in registers: sm_100 has no f64 kind for tcgen05 / TMEM),
-//     `empty` mbarriers hand the stage back; 6 stages per consumer group;
-//   * persistent CTAs (one per SM) with TWO consumer groups, each with its own producer warp and stage ring, working on
-//     64 x 64 tiles half a tile out of phase: the epilogue (global stores) of one group runs under the main loop of the
+//     `empty` mbarriers hand the stage back; 4 stages per consumer group;
+//   * persistent CTAs (one per SM) with THREE consumer groups, each with its own producer warp and stage ring, working on
+//     64 x 64 tiles a third of a tile out of phase: the epilogue (global stores) of one group runs under the main loop of the
 //     other (with independent CTAs all tiles of a wave reach their epilogue together and the tensor pipe idles: 58 %
 //     pipe-active in ncu); the tile count of the step's shapes (1024 at d = 4, chi = 128) quantises to 148 SMs at 99 %
 //     (128 x 128 tiles: 86 %);
@@ -143,7 +143,7 @@ __device__ __forceinline__ Unit unit_of(const TmaGemm& g, int u) {
   return r;
 }
 
-// Persistent CTA (one per SM): two consumer groups of four warps, each with its own ring of NSTAGE stages and its own
+// Persistent CTA (one per SM): NGRP consumer groups of four warps, each with its own ring of NSTAGE stages and its own
 // producer warp.  CTA b works on the units b, b + G, b + 2G, ... (G = grid size); group 0 takes the even ones of that
 // list, group 1 the odd ones, and group 1 starts half a tile late, so that the epilogue (global stores) of one group
 // runs under the main loop of the other and the FP64 tensor pipe always has a main loop to serve.
