@@ -144,9 +144,9 @@ __device__ __forceinline__ Unit unit_of(const TmaGemm& g, int u) {
 }
 
 // Persistent CTA (one per SM): NGRP consumer groups of four warps, each with its own ring of NSTAGE stages and its own
-// producer warp.  CTA b works on the units b, b + G, b + 2G, ... (G = grid size); group 0 takes the even ones of that
-// list, group 1 the odd ones, and group 1 starts half a tile late, so that the epilogue (global stores) of one group
-// runs under the main loop of the other and the FP64 tensor pipe always has a main loop to serve.
+// producer warp.  CTA b works on the units b, b + G, b + 2G, ... (G = grid size); group g takes every NGRP-th one of that
+// list starting with the g-th, and starts 1 / NGRP of a tile after group g - 1, so that the epilogue (global stores) of one
+// group runs under the main loops of the others and the FP64 tensor pipe always has a main loop to serve.
 template <bool AKF, bool BKF>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
