@@ -191,8 +191,8 @@ function nccl_unique_id(nccl_path::Union{Nothing,String} = nothing)
     id
 end
 comm_init(id::Vector{UInt8}, rank::Integer, nranks::Integer; nccl_path::Union{Nothing,String} = nothing) =
-    check(ccall((:tnad_comm_init, libtnad), Cint, (Ptr{Cvoid}, Cstring, Ptr{UInt8}, Cint, Cint),
-                ctx(), something(nccl_path, C_NULL), id, rank, nranks))
+    tnad_check(ccall((:tnad_comm_init, libtnad), Cint, (Ptr{Cvoid}, Cstring, Ptr{UInt8}, Cint, Cint),
+                tnad_ctx(), something(nccl_path, C_NULL), id, rank, nranks))
 
 # ctmrgstep((c, t, vals), (a, χ, D)) of src/ctmrg.jl:126-153 with the contractions sliced along χ over the ranks,
 # ncclAllGather around svd(cpmat + cpmat') and a shared back-transformation; every rank passes and receives the full
@@ -200,8 +200,30 @@ comm_init(id::Vector{UInt8}, rank::Integer, nranks::Integer; nccl_path::Union{No
 function ctmrgstep_sharded(a::Array{Float64,4}, c::Matrix{Float64}, t::Array{Float64,3})
     D, χ = size(a, 1), size(c, 1)
     c′, t′, vals = similar(c), similar(t), Vector{Float64}(undef, χ * D)
-    GC.@preserve a c t c′ t′ vals check(ccall((:tnad_ctmrgstep_sharded, libtnad), Cint,
+    GC.@preserve a c t c′ t′ vals tnad_check(ccall((:tnad_ctmrgstep_sharded, libtnad), Cint,
         (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
-        ctx(), a, D, c, t, χ, c′, t′, vals, C_NULL))
+        tnad_ctx(), a, D, c, t, χ, c′, t′, vals, C_NULL))
     c′, t′, vals
 end
+
+# ctmrg(rt; tol, maxit) (src/ctmrg.jl:110-117) over the communicator: the fixed-point loop with the reference's stop rule
+function ctmrg_sharded(a::Array{Float64,4}, c::Matrix{Float64}, t::Array{Float64,3}; tol::Real, maxit::Integer)
+    D, χ = size(a, 1), size(c, 1)
+    c′, t′, vals, steps = copy(c), copy(t), Vector{Float64}(undef, χ * D), Ref{Cint}(0)
+    GC.@preserve a c′ t′ vals tnad_check(ccall((:tnad_ctmrg_sharded, libtnad), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Ref{Cint}, Ptr{Cdouble}),
+        tnad_ctx(), a, D, χ, c′, t′, Float64(tol), maxit, steps, vals))
+    c′, t′, vals, Int(steps[])
+end
+
+# _initializect_square(bulk, Val(:random), χ) (src/ctmrg.jl:66-72) generated on the device from a seed
+function initializect_random_device(D::Integer, χ::Integer, seed::Integer)
+    c, t = Matrix{Float64}(undef, χ, χ), Array{Float64,3}(undef, χ, D, χ)
+    GC.@preserve c t tnad_check(ccall((:tnad_ctmrg_init_random, libtnad), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Culonglong, Ptr{Cdouble}, Ptr{Cdouble}), tnad_ctx(), D, χ, UInt64(seed), c, t))
+    c, t
+end
+
+# A/B switches of the context (DESIGN.md 7a), e.g. tnad_set_option("TNAD_SHARDED_LOOP", "1") after comm_init
+tnad_set_option(name::String, value::Union{Nothing,String}) =
+    ccall((:tnad_set_option, libtnad), Cint, (Ptr{Cvoid}, Cstring, Cstring), tnad_ctx(), name, something(value, C_NULL))
